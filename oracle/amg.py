@@ -1,0 +1,183 @@
+"""Smoothed-aggregation AMG, CPU restatement -- TEST INFRASTRUCTURE.
+
+The reference delegates Ap^-1 and the velocity-block solve of its "iterative"
+set-up to hypre BoomerAMG (demo_navier-stokes-pcd.py:153-160), which is neither
+vendored nor reproducible bit-wise.  BASELINE.json's north_star replaces it, on
+both sides of the comparison, by a smoothed-aggregation V-cycle whose smoother,
+restriction and prolongation are SpMV-class operations.  This module restates
+that algorithm (Vanek/Mandel/Brezina) so that the product's hierarchy and
+V-cycle can be checked to rounding:
+
+  strength     |a_ij| >= theta * sqrt(|a_ii| |a_jj|)            (i != j)
+  aggregation  greedy three-phase (root + strong neighbours; leftovers join the
+               strongest neighbouring aggregate; remaining form own aggregates);
+               rows without strong neighbours (Dirichlet rows) stay un-aggregated
+  tentative    T[i, agg(i)] = 1/sqrt(|agg|)
+  prolongator  P = (I - (4/3)/rho * D^-1 A) T, rho = power-iteration estimate of
+               rho(D^-1 A) (20 steps, fixed start vector) times 1.1
+  coarse op    A_c = P^T A P
+  smoother     Chebyshev-Jacobi of ``smooth_steps`` steps on [rho/ratio, rho] (one
+               step = damped Jacobi), same recurrence as the Mp solve
+  coarsest     dense inverse
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+
+from .petsc_algos import chebyshev_jacobi
+
+
+def start_vector(n):
+    """Deterministic pseudo-random start vector shared with the product
+    (multiplicative hash of the index), values in [0.5, 1.5)."""
+    i = np.arange(n, dtype=np.uint64)
+    h = (i * np.uint64(2654435761) + np.uint64(12345)) & np.uint64(0xFFFFFFFF)
+    return 0.5 + h.astype(np.float64) / 4294967296.0
+
+
+def estimate_rho(A, dinv, steps=20, safety=1.1):
+    v = start_vector(A.shape[0])
+    v /= np.linalg.norm(v)
+    rho = 0.0
+    for _ in range(steps):
+        w = dinv * (A @ v)
+        rho = float(np.linalg.norm(w))
+        if rho == 0.0:
+            return 1.0
+        v = w / rho
+    return safety * rho
+
+
+def strength_graph(A, theta):
+    """CSR boolean graph of strong off-diagonal connections."""
+    A = A.tocsr()
+    d = np.abs(A.diagonal())
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    cols = A.indices
+    strong = (rows != cols) & (np.abs(A.data) >= theta * np.sqrt(d[rows] * d[cols])) & (A.data != 0.0)
+    S = sp.csr_matrix((np.abs(A.data[strong]), (rows[strong], cols[strong])), shape=A.shape)
+    S.sort_indices()
+    return S
+
+
+def aggregate_greedy(S):
+    """Three-phase greedy aggregation on the strength graph S (CSR, values =
+    |a_ij|).  Returns agg[n] (aggregate id or -1) and the number of aggregates."""
+    n = S.shape[0]
+    ip, ix, vals = S.indptr, S.indices, S.data
+    agg = np.full(n, -1, dtype=np.int64)
+    nagg = 0
+    has_nb = np.diff(ip) > 0
+    # phase 1: root i with all strong neighbours still free
+    for i in range(n):
+        if agg[i] != -1 or not has_nb[i]:
+            continue
+        nb = ix[ip[i]:ip[i + 1]]
+        if np.all(agg[nb] == -1):
+            agg[i] = nagg
+            agg[nb] = nagg
+            nagg += 1
+    # phase 2: leftovers join the aggregate of their strongest phase-1 neighbour
+    agg1 = agg.copy()
+    for i in range(n):
+        if agg[i] != -1 or not has_nb[i]:
+            continue
+        best, bestv = -1, -1.0
+        for k in range(ip[i], ip[i + 1]):
+            j = ix[k]
+            if agg1[j] != -1 and vals[k] > bestv:
+                best, bestv = agg1[j], vals[k]
+        if best != -1:
+            agg[i] = best
+    # phase 3: whatever is left forms aggregates with its free neighbours
+    for i in range(n):
+        if agg[i] != -1 or not has_nb[i]:
+            continue
+        agg[i] = nagg
+        for k in range(ip[i], ip[i + 1]):
+            j = ix[k]
+            if agg[j] == -1 and has_nb[j]:
+                agg[j] = nagg
+        nagg += 1
+    return agg, nagg
+
+
+def tentative_prolongator(agg, nagg):
+    n = agg.size
+    rows = np.flatnonzero(agg >= 0)
+    cols = agg[rows]
+    counts = np.bincount(cols, minlength=nagg).astype(np.float64)
+    vals = 1.0 / np.sqrt(counts[cols])
+    T = sp.csr_matrix((vals, (rows, cols)), shape=(n, nagg))
+    return T
+
+
+@dataclass
+class Level:
+    A: sp.csr_matrix
+    dinv: np.ndarray
+    rho: float
+    P: sp.csr_matrix | None = None     # to this level from the next coarser one
+    R: sp.csr_matrix | None = None
+
+
+@dataclass
+class Hierarchy:
+    levels: list = field(default_factory=list)
+    coarse_inv: np.ndarray | None = None
+    smooth_steps: int = 2
+    eig_ratio: float = 10.0
+
+    def operator_complexity(self):
+        return sum(l.A.nnz for l in self.levels) / self.levels[0].A.nnz
+
+    def _smooth(self, lvl, b):
+        return chebyshev_jacobi(lvl.A, lvl.dinv, b, lvl.rho / self.eig_ratio, lvl.rho, self.smooth_steps)
+
+    def vcycle(self, b, k=0):
+        """One V-cycle with zero initial guess on level k."""
+        lvl = self.levels[k]
+        if k == len(self.levels) - 1:
+            return self.coarse_inv @ b
+        x = self._smooth(lvl, b)                 # pre-smoothing from zero guess
+        r = b - lvl.A @ x
+        x = x + lvl.P @ self.vcycle(lvl.R @ r, k + 1)
+        r = b - lvl.A @ x
+        return x + self._smooth(lvl, r)          # post-smoothing on the correction equation
+
+    def __call__(self, b):
+        return self.vcycle(b)
+
+
+def build_hierarchy(A, theta=0.08, max_levels=12, coarse_size=400, smooth_steps=2,
+                    eig_ratio=10.0, omega_scale=4.0 / 3.0):
+    H = Hierarchy(smooth_steps=smooth_steps, eig_ratio=eig_ratio)
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    while True:
+        diag = A.diagonal()
+        dinv = np.where(diag != 0.0, 1.0 / np.where(diag != 0.0, diag, 1.0), 0.0)
+        rho = estimate_rho(A, dinv)
+        lvl = Level(A=A, dinv=dinv, rho=rho)
+        H.levels.append(lvl)
+        if A.shape[0] <= coarse_size or len(H.levels) >= max_levels:
+            break
+        S = strength_graph(A, theta * 0.5 ** (len(H.levels) - 1))
+        agg, nagg = aggregate_greedy(S)
+        if nagg == 0 or nagg >= A.shape[0]:
+            break
+        T = tentative_prolongator(agg, nagg)
+        omega = omega_scale / rho
+        P = (T - omega * (sp.diags(dinv) @ (A @ T))).tocsr()
+        P.sort_indices()
+        R = P.T.tocsr()
+        R.sort_indices()
+        Ac = (R @ (A @ P)).tocsr()
+        Ac.sort_indices()
+        lvl.P, lvl.R = P, R
+        A = Ac
+    H.coarse_inv = np.linalg.inv(H.levels[-1].A.toarray())
+    return H
