@@ -1,0 +1,14 @@
+"""fenapack_b200 -- B200-native implementation of FENaPack's hot path: the PCD
+block-triangular preconditioner inside right-preconditioned (F)GMRES for the
+P2/P1 Oseen / Navier-Stokes system.
+
+``capi``            ctypes binding of libfenapack_cuda.so (the C ABI, include/fenapack_cuda.h)
+``preconditioners`` PCDPC_BRM1 / PCDPC_BRM2 python-PC contexts (reference: fenapack/preconditioners.py)
+``field_split``     PCDKSP / PCDKrylovSolver                  (reference: fenapack/field_split.py)
+``field_split_backend`` PCDInterface                          (reference: fenapack/field_split_backend.py)
+``assembling``      PCDAssembler / PCDForm                    (reference: fenapack/assembling.py)
+``nonlinear_solvers`` PCDNewtonSolver / PCDNonlinearProblem   (reference: fenapack/nonlinear_solvers.py)
+
+The CUDA library is mandatory; nothing here falls back to the CPU.
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,125 @@
+// Device side of the inner solvers: Chebyshev-Jacobi sweeps (the Mp solve of the
+// reference's "iterative" set-up, demo_navier-stokes-pcd.py:161-165, and the AMG
+// smoother) and the smoothed-aggregation V-cycle that stands in for hypre
+// BoomerAMG (demo_navier-stokes-pcd.py:153-160).  Every step is one SpMV-class
+// kernel with a fused epilogue (kernels.cu).
+#include <cmath>
+
+#include "fnp_internal.cuh"
+
+namespace fnp {
+
+// KSPCHEBYSHEV + PCJACOBI recurrence (PETSc cheby.c, recalled -- SURVEY 8a row 9):
+//   s = 2/(emax+emin), alpha = 1 - s emin, mu = 1/alpha, omegaprod = 2/alpha, c0 = 1, c1 = mu
+//   p1 = s D^-1 b
+//   pass: c2 = 2 mu c1 - c0; omega = omegaprod c1/c2; p2 = (1-omega) p0 + omega p1 + omega s D^-1 (b - A p1)
+// `steps` = number of Jacobi applications.  Result: out = add + out_scale * p_last.
+void cheb_jacobi(Ctx &c, const DevCsr &A, const double *b, double emin, double emax, int steps, double out_scale,
+                 const double *add, double *out, double *w0, double *w1) {
+  FNP_REQUIRE(A.has_dinv, FNP_ERR_STATE, "Chebyshev-Jacobi: operator has no Jacobi diagonal (fnp_setup missing)");
+  FNP_REQUIRE(steps >= 1, FNP_ERR_ARG, "Chebyshev-Jacobi needs ksp_max_it >= 1");
+  const int64_t n = A.nrows;
+  const double s = 2.0 / (emax + emin);
+  const double alpha = 1.0 - s * emin;
+  const double mu = 1.0 / alpha;
+  const double omegaprod = 2.0 / alpha;
+  if (steps == 1) {
+    vec_pointwise_scale(c, n, s * out_scale, A.dinv.p, b, add, out);
+    return;
+  }
+  // rotating buffers; the last pass writes straight into `out`
+  double *buf[2] = {w0, w1};
+  double *p0 = nullptr;
+  double *p1 = buf[0];
+  vec_pointwise_scale(c, n, s, A.dinv.p, b, nullptr, p1);
+  double c0 = 1.0, c1 = mu;
+  for (int pass = 1; pass < steps; ++pass) {
+    const double c2 = 2.0 * mu * c1 - c0;
+    const double omega = omegaprod * c1 / c2;
+    const bool last = pass == steps - 1;
+    double *p2 = last ? out : (p0 ? p0 : buf[1]);
+    const double sc = last ? out_scale : 1.0;
+    EpiCheb e;
+    e.out = p2;
+    e.p0 = p0;
+    e.p1 = p1;
+    e.b = b;
+    e.dinv = A.dinv.p;
+    e.add = last ? add : nullptr;
+    e.c0 = sc * (1.0 - omega);
+    e.c1 = sc * omega;
+    e.c2 = sc * omega * s;
+    spmv_cheb(c, A, e);
+    p0 = p1;
+    p1 = p2;
+    c0 = c1;
+    c1 = c2;
+  }
+}
+
+static void upload_csr(Ctx &c, const HostCsr &h, DevCsr &d) {
+  d.nrows = (int32_t)h.nrows;
+  d.ncols_own = (int32_t)h.ncols;
+  d.nghost = 0;
+  d.nnz = h.nnz();
+  d.rowptr.upload(h.rowptr.data(), h.rowptr.size(), c.stream);
+  d.col.upload(h.col.data(), h.col.size(), c.stream);
+  d.val.upload(h.val.data(), h.val.size(), c.stream);
+  d.mean_row = h.nrows ? (double)d.nnz / (double)h.nrows : 0.0;
+  int lanes = 2;
+  while (lanes < 32 && lanes * 2 < d.mean_row + 0.5) lanes *= 2;
+  d.lanes = lanes;
+}
+
+void amg_upload(Ctx &c, DevHierarchy &H) {
+  const size_t L = H.host.levels.size();
+  H.levels.clear();
+  H.levels.resize(L);
+  for (size_t l = 0; l < L; ++l) {
+    const HostLevel &hl = H.host.levels[l];
+    DevLevel &dl = H.levels[l];
+    upload_csr(c, hl.A, dl.A);
+    dl.A.dinv.upload(hl.dinv.data(), hl.dinv.size(), c.stream);
+    dl.A.has_dinv = true;
+    dl.rho = hl.rho;
+    if (l + 1 < L) {
+      upload_csr(c, hl.P, dl.P);
+      upload_csr(c, hl.R, dl.R);
+    }
+    const size_t n = (size_t)hl.A.nrows;
+    dl.x.alloc(n); dl.b.alloc(n); dl.r.alloc(n); dl.w0.alloc(n); dl.w1.alloc(n);
+  }
+  H.coarse_n = (int)H.host.levels.back().A.nrows;
+  H.coarse_inv.upload(H.host.coarse_inv.data(), H.host.coarse_inv.size(), c.stream);
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  H.built = true;
+}
+
+static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, double *x) {
+  DevLevel &L = H.levels[l];
+  if (l + 1 == H.levels.size()) {
+    dense_gemv(c, H.coarse_n, H.coarse_inv.p, b, x);
+    return;
+  }
+  const AmgParams &p = H.params;
+  const double emax = L.rho, emin = L.rho / p.eig_ratio;
+  DevLevel &C = H.levels[l + 1];
+  // pre-smoothing from the zero initial guess
+  cheb_jacobi(c, L.A, b, emin, emax, p.smooth_steps, 1.0, nullptr, x, L.w0.p, L.w1.p);
+  // r = b - A x ; b_c = R r
+  spmv_axpby(c, L.A, x, -1.0, 1.0, b, L.r.p);
+  spmv_store(c, L.R, L.r.p, C.b.p);
+  vcycle_level(c, H, l + 1, C.b.p, C.x.p);
+  // x += P x_c
+  spmv_axpby(c, L.P, C.x.p, 1.0, 1.0, x, x);
+  // post-smoothing on the correction equation: x += cheb(A, b - A x)
+  spmv_axpby(c, L.A, x, -1.0, 1.0, b, L.r.p);
+  cheb_jacobi(c, L.A, L.r.p, emin, emax, p.smooth_steps, 1.0, x, x, L.w0.p, L.w1.p);
+}
+
+void amg_vcycle(Ctx &c, DevHierarchy &H, const double *b, double *x) {
+  FNP_REQUIRE(H.built, FNP_ERR_STATE, "AMG hierarchy not built (fnp_setup missing)");
+  vcycle_level(c, H, 0, b, x);
+}
+
+}  // namespace fnp

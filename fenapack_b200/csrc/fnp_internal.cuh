@@ -1,0 +1,326 @@
+// Internal declarations of libfenapack_cuda (sm_100a).  Not part of the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fenapack_cuda.h"
+
+namespace fnp {
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string &m);
+
+#define FNP_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      throw ::fnp::Error(FNP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + \
+                                           " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+// NCCL entry points, bound with dlopen on first use (nccl_shim.cu)
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+const NcclApi &nccl();
+
+#define FNP_NCCL(call)                                                                               \
+  do {                                                                                               \
+    ncclResult_t r_ = (call);                                                                        \
+    if (r_ != ncclSuccess)                                                                           \
+      throw ::fnp::Error(FNP_ERR_NCCL, std::string(#call) + ": " + ::fnp::nccl().GetErrorString(r_)); \
+  } while (0)
+
+#define FNP_REQUIRE(cond, code, msg)                 \
+  do {                                               \
+    if (!(cond)) throw ::fnp::Error((code), (msg));  \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// device memory
+// ---------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t count) { alloc(count); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) FNP_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T)));
+  }
+  void ensure(size_t count) { if (count > n) alloc(count); }
+  void upload(const T *h, size_t count, cudaStream_t s) {
+    ensure(count);
+    if (count) FNP_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void zero(cudaStream_t s) { if (n) FNP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+// ---------------------------------------------------------------------------
+// host CSR (set-up side) and device CSR (apply side)
+// ---------------------------------------------------------------------------
+struct HostCsr {
+  int64_t nrows = 0, ncols = 0;
+  std::vector<int32_t> rowptr, col;
+  std::vector<double> val;
+  int64_t nnz() const { return rowptr.empty() ? 0 : rowptr.back(); }
+};
+
+struct Ctx;
+
+// Device-resident CSR operator; columns index [x_own | x_ghost].
+struct DevCsr {
+  int32_t nrows = 0;
+  int32_t ncols_own = 0;     // columns [0, ncols_own) address the owned part of x
+  int32_t nghost = 0;        // columns [ncols_own, ncols_own+nghost) address the ghost buffer
+  int64_t nnz = 0;
+  int lanes = 8;             // lanes per row of the vector kernel, from the row-length histogram
+  DevBuf<int32_t> rowptr, col;
+  DevBuf<double> val, dinv;
+  bool has_dinv = false;
+  double mean_row = 0.0, max_row = 0.0;
+  // algorithmic bytes of one y = A x  (SURVEY 8d): 12 nnz + 4 (rows+1) + 8 rows + 8 cols
+  double spmv_bytes() const {
+    return 12.0 * nnz + 4.0 * (nrows + 1) + 8.0 * nrows + 8.0 * (ncols_own + nghost);
+  }
+};
+
+// epilogues of the SpMV-class kernels ---------------------------------------
+struct EpiStore {            // y = A x
+  double *y;
+};
+struct EpiAxpby {            // y = a * (A x) + b * z          (z may alias y)
+  double *y;
+  const double *z;
+  double a, b;
+};
+struct EpiCheb {             // out = add + c0 p0 + c1 p1 + c2 dinv (b - A p1)   (p0, add optional)
+  double *out;
+  const double *p0, *p1, *b, *dinv, *add;
+  double c0, c1, c2;
+};
+
+void spmv_store(Ctx &c, const DevCsr &A, const double *x, double *y);
+void spmv_axpby(Ctx &c, const DevCsr &A, const double *x, double a, double b, const double *z, double *y);
+void spmv_cheb(Ctx &c, const DevCsr &A, const EpiCheb &e);
+
+// BLAS-1 class kernels ------------------------------------------------------
+void vec_copy(Ctx &c, int64_t n, const double *x, double *y);
+void vec_scale(Ctx &c, int64_t n, double a, double *x);                       // x *= a
+void vec_axpy(Ctx &c, int64_t n, double a, const double *x, double *y);       // y += a x
+void vec_axpby(Ctx &c, int64_t n, double a, const double *x, double b, const double *y, double *out);
+void vec_zero(Ctx &c, int64_t n, double *x);
+void vec_pointwise_scale(Ctx &c, int64_t n, double s, const double *d, const double *b, const double *add, double *out); // out = add + s d b
+void vec_copy_bc(Ctx &c, int64_t n, const double *x, double *z, const int32_t *idx, const double *val, int32_t nbc);
+void vec_scatter_bc(Ctx &c, double *z, const int32_t *idx, const double *val, int32_t nbc);
+void vec_gather(Ctx &c, int64_t n, const int64_t *idx, const double *src, double *dst);   // dst[i] = src[idx[i]]
+void vec_scatter(Ctx &c, int64_t n, const int64_t *idx, const double *src, double *dst);  // dst[idx[i]] = src[i]
+void extract_diag_inv(Ctx &c, DevCsr &A);
+
+// deterministic reductions (two-stage, no atomics); results land in device memory.
+// Vptrs_dev: device array of pointers to the basis vectors (allocated lazily).
+// h[i] = v_i . w for i < nvec
+void multi_dot_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int nvec, const double *w, double *h_dev);
+// w -= sum_i h[i] v_i ; nrm2_dev[0] = ||w||^2 (after the update)
+void multi_axpy_norm_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int nvec, const double *h_dev, double *w,
+                          double *nrm2_dev);
+// x += sum_i y[i] Z_i (y on device)
+void multi_axpy_ptrs(Ctx &c, int64_t n, const double *const *Zptrs_dev, int nvec, const double *y_dev, double *x);
+// v = w / sqrt(nrm2_dev[0])
+void vec_scale_inv_sqrt(Ctx &c, int64_t n, const double *nrm2_dev, const double *w, double *v);
+void dot(Ctx &c, int64_t n, const double *x, const double *y, double *out_dev);
+void dense_gemv(Ctx &c, int n, const double *Minv, const double *b, double *x);
+
+// ---------------------------------------------------------------------------
+// AMG
+// ---------------------------------------------------------------------------
+struct AmgParams {
+  double theta = 0.08;
+  int max_levels = 12;
+  int coarse_size = 400;
+  int smooth_steps = 2;
+  double eig_ratio = 10.0;
+  double omega_scale = 4.0 / 3.0;
+};
+
+struct HostLevel {
+  HostCsr A, P, R;
+  std::vector<double> dinv;
+  double rho = 1.0;
+};
+
+struct HostHierarchy {
+  std::vector<HostLevel> levels;
+  std::vector<double> coarse_inv;   // dense row-major
+};
+
+void amg_build_host(const HostCsr &A, const AmgParams &p, HostHierarchy &H);
+
+struct DevLevel {
+  DevCsr A, P, R;
+  double rho = 1.0;
+  DevBuf<double> x, b, r, w0, w1;
+};
+
+struct DevHierarchy {
+  std::vector<DevLevel> levels;
+  DevBuf<double> coarse_inv;
+  int coarse_n = 0;
+  AmgParams params;
+  HostHierarchy host;     // kept for introspection / refresh
+  bool built = false;
+};
+
+void amg_upload(Ctx &c, DevHierarchy &H);
+// x = Vcycle(b), zero initial guess; b and x are level-0 sized device vectors (may not alias)
+void amg_vcycle(Ctx &c, DevHierarchy &H, const double *b, double *x);
+
+// Chebyshev-Jacobi, zero initial guess, `steps` Jacobi applications:
+//   out = add + out_scale * cheb(A, b)
+void cheb_jacobi(Ctx &c, const DevCsr &A, const double *b, double emin, double emax, int steps,
+                 double out_scale, const double *add, double *out, double *w0, double *w1);
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+enum KspType { KSP_PREONLY = 0, KSP_RICHARDSON, KSP_CHEBYSHEV, KSP_CG };
+enum PcType { PC_NONE = 0, PC_JACOBI, PC_AMG };
+
+struct InnerOpts {
+  KspType ksp = KSP_RICHARDSON;
+  PcType pc = PC_AMG;
+  int max_it = 1;
+  double rtol = 0.0;
+  double emin = 0.5, emax = 2.0;
+  AmgParams amg;
+};
+
+struct Timer {
+  double ms = 0.0;
+  int64_t calls = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  int64_t launches = 0;
+
+  // distributed
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+
+  // layout
+  bool have_layout = false;
+  int64_t n_u = 0, u_begin = 0, n_u_global = 0;
+  int64_t n_p = 0, p_begin = 0, n_p_global = 0;
+
+  // options
+  int variant = FNP_MAT_COUNT;  // set in ctor
+  bool flexible = true;
+  int restart = 150;
+  double rtol = 1e-6, atol = 1e-50;
+  int max_it = 10000;
+  InnerOpts opt_u, opt_ap, opt_mp;
+  bool timers_on = false;
+
+  // operators
+  HostCsr hmat[FNP_MAT_COUNT];          // sorted host copies (pattern always; values for AMG operators)
+  std::vector<int64_t> perm[FNP_MAT_COUNT];   // user order -> sorted order (empty = identity)
+  bool have_pattern[FNP_MAT_COUNT] = {};
+  bool have_values[FNP_MAT_COUNT] = {};
+  bool dirty[FNP_MAT_COUNT] = {};
+  DevCsr dmat[FNP_MAT_COUNT];
+  DevBuf<int32_t> bc_idx;
+  DevBuf<double> bc_val;
+  int32_t nbc = 0;
+  DevBuf<int64_t> is_u, is_p;
+  bool have_is = false;
+  bool is_setup = false;
+
+  DevHierarchy amg_u, amg_ap;
+
+  // work space
+  DevBuf<double> p_w[6];      // pressure-sized work vectors
+  DevBuf<double> u_w[5];      // velocity-sized work vectors
+  DevBuf<double> red_partial; // block partials of reductions
+  DevBuf<double> red_out;     // small device results (h column, norms, CG scalars)
+  double *pinned = nullptr;   // host-pinned mirror of red_out
+  size_t pinned_n = 0;
+  DevBuf<double> io[4];       // staging for host-pointer calls
+
+  // Krylov basis
+  std::vector<DevBuf<double>> V, Z;
+  DevBuf<double> kr_w, kr_x, kr_b;
+  std::vector<double> res_hist;
+
+  // timers
+  std::map<std::string, Timer> timers;
+  cudaEvent_t ev_tic = nullptr, ev_toc = nullptr;
+
+  explicit Ctx(int dev);
+  ~Ctx();
+  const DevCsr &velocity_pc_matrix() const { return have_values[FNP_MAT_P00] ? dmat[FNP_MAT_P00] : dmat[FNP_MAT_A00]; }
+  int velocity_pc_index() const { return have_values[FNP_MAT_P00] ? FNP_MAT_P00 : FNP_MAT_A00; }
+};
+
+// scoped stage timer (CUDA events on the context stream); no-op unless timers_on
+struct StageTimer {
+  Ctx &c;
+  const char *name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  StageTimer(Ctx &ctx, const char *nm);
+  ~StageTimer();
+};
+
+// solver pieces (pcd.cu / gmres.cu)
+void setup_all(Ctx &c);
+void mp_solve(Ctx &c, const double *b, double out_scale, const double *add, double *x);
+void ap_solve(Ctx &c, const double *b, double *x);
+void u_solve(Ctx &c, const double *b, double *x);
+void schur_apply(Ctx &c, const double *x_p, double *y_p);
+void pc_apply(Ctx &c, const double *x_u, const double *x_p, double *y_u, double *y_p);
+void system_matvec(Ctx &c, const double *x, double *y);   // split vectors [u;p]
+void solve_fgmres(Ctx &c, const double *b, double *x, int32_t *its, double *rnorm, int32_t *napply);
+
+}  // namespace fnp

@@ -1,0 +1,360 @@
+// SpMV-class and BLAS-1-class kernels of libfenapack_cuda (sm_100a, fp64).
+//
+// Every stage of the PCD apply is HBM-bound (0.17 flop/byte for CSR SpMV), so
+// the kernels are organised around memory traffic only:
+//   * spmv_kernel<LANES, Epi>: a sub-warp of LANES threads per row (LANES chosen
+//     from the operator's row-length histogram), coalesced (col,val) streams,
+//     two independent partial sums per lane for memory-level parallelism,
+//     warp-shuffle segmented reduction, and a fused epilogue so that residuals,
+//     Chebyshev three-term updates and prolongation corrections never cost a
+//     second pass over the vectors.
+//   * reductions are two-stage and atomic-free: bit-reproducible run to run.
+#include "fnp_internal.cuh"
+
+namespace fnp {
+
+static inline int blocks_for(const Ctx &c, int64_t n, int threads, int per_sm) {
+  int64_t b = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)c.num_sms * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+#define FNP_LAUNCH_CHECK(c)            \
+  do {                                 \
+    (c).launches++;                    \
+    FNP_CUDA(cudaPeekAtLastError());   \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// SpMV
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue(const EpiStore &e, int r, double s) { e.y[r] = s; }
+__device__ __forceinline__ void epilogue(const EpiAxpby &e, int r, double s) {
+  e.y[r] = e.a * s + e.b * e.z[r];
+}
+__device__ __forceinline__ void epilogue(const EpiCheb &e, int r, double s) {
+  double v = e.c1 * e.p1[r] + e.c2 * e.dinv[r] * (e.b[r] - s);
+  if (e.p0) v += e.c0 * e.p0[r];
+  if (e.add) v += e.add[r];
+  e.out[r] = v;
+}
+
+template <int LANES, class Epi>
+__global__ void __launch_bounds__(256)
+spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+            const double *__restrict__ val, const double *__restrict__ x, Epi epi) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = tid / LANES;
+  const int lane = tid % LANES;
+  double s0 = 0.0, s1 = 0.0;
+  if (row < nrows) {
+    const int beg = rowptr[row], end = rowptr[row + 1];
+    int k = beg + lane;
+    for (; k + LANES < end; k += 2 * LANES) {
+      const int c0 = __ldg(col + k), c1 = __ldg(col + k + LANES);
+      const double v0 = __ldg(val + k), v1 = __ldg(val + k + LANES);
+      s0 += v0 * __ldg(x + c0);
+      s1 += v1 * __ldg(x + c1);
+    }
+    if (k < end) s0 += __ldg(val + k) * __ldg(x + __ldg(col + k));
+  }
+  double s = s0 + s1;
+#pragma unroll
+  for (int off = LANES / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, LANES);
+  if (row < nrows && lane == 0) epilogue(epi, row, s);
+}
+
+template <class Epi>
+static void spmv_launch(Ctx &c, const DevCsr &A, const double *x, const Epi &epi) {
+  if (A.nrows == 0) return;
+  const int threads = 256;
+  auto grid = [&](int lanes) { return (int)(((int64_t)A.nrows * lanes + threads - 1) / threads); };
+  switch (A.lanes) {
+    case 2: spmv_kernel<2, Epi><<<grid(2), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, epi); break;
+    case 4: spmv_kernel<4, Epi><<<grid(4), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, epi); break;
+    case 8: spmv_kernel<8, Epi><<<grid(8), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, epi); break;
+    case 16: spmv_kernel<16, Epi><<<grid(16), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, epi); break;
+    default: spmv_kernel<32, Epi><<<grid(32), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, epi); break;
+  }
+  FNP_LAUNCH_CHECK(c);
+}
+
+void spmv_store(Ctx &c, const DevCsr &A, const double *x, double *y) { spmv_launch(c, A, x, EpiStore{y}); }
+void spmv_axpby(Ctx &c, const DevCsr &A, const double *x, double a, double b, const double *z, double *y) {
+  spmv_launch(c, A, x, EpiAxpby{y, z, a, b});
+}
+void spmv_cheb(Ctx &c, const DevCsr &A, const EpiCheb &e) { spmv_launch(c, A, e.p1, e); }
+
+__global__ void diag_inv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                const double *__restrict__ val, double *__restrict__ dinv) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  double d = 0.0;
+  for (int k = rowptr[r]; k < rowptr[r + 1]; ++k)
+    if (col[k] == r) d = val[k];
+  dinv[r] = d != 0.0 ? 1.0 / d : 0.0;
+}
+
+void extract_diag_inv(Ctx &c, DevCsr &A) {
+  A.dinv.ensure(A.nrows);
+  if (A.nrows) {
+    diag_inv_kernel<<<(A.nrows + 255) / 256, 256, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, A.dinv.p);
+    FNP_LAUNCH_CHECK(c);
+  }
+  A.has_dinv = true;
+}
+
+// ---------------------------------------------------------------------------
+// BLAS-1 class
+// ---------------------------------------------------------------------------
+#define GRID_STRIDE(i, n) \
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+__global__ void copy_kernel(int64_t n, const double *__restrict__ x, double *__restrict__ y) { GRID_STRIDE(i, n) y[i] = x[i]; }
+__global__ void scale_kernel(int64_t n, double a, double *x) { GRID_STRIDE(i, n) x[i] *= a; }
+__global__ void axpy_kernel(int64_t n, double a, const double *__restrict__ x, double *y) { GRID_STRIDE(i, n) y[i] += a * x[i]; }
+__global__ void axpby_kernel(int64_t n, double a, const double *x, double b, const double *y, double *out) {
+  GRID_STRIDE(i, n) out[i] = a * x[i] + b * y[i];
+}
+__global__ void zero_kernel(int64_t n, double *x) { GRID_STRIDE(i, n) x[i] = 0.0; }
+__global__ void pw_scale_kernel(int64_t n, double s, const double *__restrict__ d, const double *__restrict__ b,
+                                const double *add, double *out) {
+  GRID_STRIDE(i, n) {
+    double v = s * d[i] * b[i];
+    if (add) v += add[i];
+    out[i] = v;
+  }
+}
+__global__ void scatter_bc_kernel(double *z, const int32_t *__restrict__ idx, const double *__restrict__ val, int32_t n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) z[idx[i]] = val[i];
+}
+__global__ void gather_kernel(int64_t n, const int64_t *__restrict__ idx, const double *__restrict__ src, double *__restrict__ dst) {
+  GRID_STRIDE(i, n) dst[i] = src[idx[i]];
+}
+__global__ void scatter_kernel(int64_t n, const int64_t *__restrict__ idx, const double *__restrict__ src, double *__restrict__ dst) {
+  GRID_STRIDE(i, n) dst[idx[i]] = src[i];
+}
+
+#define VEC_LAUNCH(kern, n, ...)                                            \
+  do {                                                                      \
+    if ((n) > 0) {                                                          \
+      kern<<<blocks_for(c, (n), 256, 16), 256, 0, c.stream>>>(__VA_ARGS__); \
+      FNP_LAUNCH_CHECK(c);                                                  \
+    }                                                                       \
+  } while (0)
+
+void vec_copy(Ctx &c, int64_t n, const double *x, double *y) { VEC_LAUNCH(copy_kernel, n, n, x, y); }
+void vec_scale(Ctx &c, int64_t n, double a, double *x) { VEC_LAUNCH(scale_kernel, n, n, a, x); }
+void vec_axpy(Ctx &c, int64_t n, double a, const double *x, double *y) { VEC_LAUNCH(axpy_kernel, n, n, a, x, y); }
+void vec_axpby(Ctx &c, int64_t n, double a, const double *x, double b, const double *y, double *out) {
+  VEC_LAUNCH(axpby_kernel, n, n, a, x, b, y, out);
+}
+void vec_zero(Ctx &c, int64_t n, double *x) { VEC_LAUNCH(zero_kernel, n, n, x); }
+void vec_pointwise_scale(Ctx &c, int64_t n, double s, const double *d, const double *b, const double *add, double *out) {
+  VEC_LAUNCH(pw_scale_kernel, n, n, s, d, b, add, out);
+}
+void vec_scatter_bc(Ctx &c, double *z, const int32_t *idx, const double *val, int32_t nbc) {
+  if (nbc > 0) {
+    scatter_bc_kernel<<<(nbc + 255) / 256, 256, 0, c.stream>>>(z, idx, val, nbc);
+    FNP_LAUNCH_CHECK(c);
+  }
+}
+void vec_copy_bc(Ctx &c, int64_t n, const double *x, double *z, const int32_t *idx, const double *val, int32_t nbc) {
+  vec_copy(c, n, x, z);
+  vec_scatter_bc(c, z, idx, val, nbc);
+}
+void vec_gather(Ctx &c, int64_t n, const int64_t *idx, const double *src, double *dst) { VEC_LAUNCH(gather_kernel, n, n, idx, src, dst); }
+void vec_scatter(Ctx &c, int64_t n, const int64_t *idx, const double *src, double *dst) { VEC_LAUNCH(scatter_kernel, n, n, idx, src, dst); }
+
+// ---------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------
+constexpr int RED_THREADS = 256;
+constexpr int DOT_BATCH = 8;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// stage 1: partial[(i) * gridDim.x + blockIdx.x] = sum over this block's elements of V_i[e] * w[e]
+__global__ void __launch_bounds__(RED_THREADS)
+multidot_kernel(int64_t n, const double *const *__restrict__ V, int nvec, const double *__restrict__ w,
+                double *__restrict__ partial) {
+  const int i0 = blockIdx.y * DOT_BATCH;
+  const double *v[DOT_BATCH];
+#pragma unroll
+  for (int b = 0; b < DOT_BATCH; ++b) v[b] = V[min(i0 + b, nvec - 1)];
+  double acc[DOT_BATCH];
+#pragma unroll
+  for (int b = 0; b < DOT_BATCH; ++b) acc[b] = 0.0;
+  GRID_STRIDE(e, n) {
+    const double wv = w[e];
+#pragma unroll
+    for (int b = 0; b < DOT_BATCH; ++b) acc[b] += __ldg(v[b] + e) * wv;
+  }
+  __shared__ double sm[DOT_BATCH][RED_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int b = 0; b < DOT_BATCH; ++b) {
+    double s = warp_sum(acc[b]);
+    if (lane == 0) sm[b][wid] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < DOT_BATCH) {
+    const int b = threadIdx.x;
+    if (i0 + b < nvec) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < RED_THREADS / 32; ++k) s += sm[b][k];
+      partial[(int64_t)(i0 + b) * gridDim.x + blockIdx.x] = s;
+    }
+  }
+}
+
+// stage 2: out[i] = sum_k partial[i * nblk + k], fixed order
+__global__ void __launch_bounds__(128)
+reduce_partials_kernel(const double *__restrict__ partial, int nblk, double *__restrict__ out) {
+  const int i = blockIdx.x;
+  double s = 0.0;
+  for (int k = threadIdx.x; k < nblk; k += blockDim.x) s += partial[(int64_t)i * nblk + k];
+  __shared__ double sm[4];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) out[i] = sm[0] + sm[1] + sm[2] + sm[3];
+}
+
+static int red_blocks(const Ctx &c, int64_t n) { return blocks_for(c, n, RED_THREADS, 4); }
+
+void multi_dot_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int nvec, const double *w, double *h_dev) {
+  if (nvec <= 0) return;
+  const int nblk = red_blocks(c, n);
+  c.red_partial.ensure((size_t)nblk * (nvec + DOT_BATCH));
+  dim3 grid(nblk, (nvec + DOT_BATCH - 1) / DOT_BATCH);
+  multidot_kernel<<<grid, RED_THREADS, 0, c.stream>>>(n, Vptrs_dev, nvec, w, c.red_partial.p);
+  FNP_LAUNCH_CHECK(c);
+  reduce_partials_kernel<<<nvec, 128, 0, c.stream>>>(c.red_partial.p, nblk, h_dev);
+  FNP_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+dot_kernel(int64_t n, const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ partial) {
+  double acc = 0.0;
+  GRID_STRIDE(e, n) acc += x[e] * y[e];
+  __shared__ double sm[RED_THREADS / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < RED_THREADS / 32; ++k) s += sm[k];
+    partial[blockIdx.x] = s;
+  }
+}
+
+void dot(Ctx &c, int64_t n, const double *x, const double *y, double *out_dev) {
+  const int nblk = red_blocks(c, n);
+  c.red_partial.ensure((size_t)nblk);
+  dot_kernel<<<nblk, RED_THREADS, 0, c.stream>>>(n, x, y, c.red_partial.p);
+  FNP_LAUNCH_CHECK(c);
+  reduce_partials_kernel<<<1, 128, 0, c.stream>>>(c.red_partial.p, nblk, out_dev);
+  FNP_LAUNCH_CHECK(c);
+}
+
+// w -= sum_i h[i] V_i, partial = block sums of w_new^2
+__global__ void __launch_bounds__(RED_THREADS)
+maxpy_norm_kernel(int64_t n, const double *const *__restrict__ V, int nvec, const double *__restrict__ h,
+                  double *__restrict__ w, double *__restrict__ partial) {
+  extern __shared__ double sh[];          // nvec coefficients
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) sh[i] = h[i];
+  __syncthreads();
+  double acc = 0.0;
+  GRID_STRIDE(e, n) {
+    double wv = w[e];
+    int i = 0;
+    for (; i + 4 <= nvec; i += 4) {
+      const double a0 = __ldg(V[i] + e), a1 = __ldg(V[i + 1] + e), a2 = __ldg(V[i + 2] + e), a3 = __ldg(V[i + 3] + e);
+      wv -= sh[i] * a0;
+      wv -= sh[i + 1] * a1;
+      wv -= sh[i + 2] * a2;
+      wv -= sh[i + 3] * a3;
+    }
+    for (; i < nvec; ++i) wv -= sh[i] * __ldg(V[i] + e);
+    w[e] = wv;
+    acc += wv * wv;
+  }
+  __shared__ double sm[RED_THREADS / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < RED_THREADS / 32; ++k) s += sm[k];
+    partial[blockIdx.x] = s;
+  }
+}
+
+void multi_axpy_norm_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int nvec, const double *h_dev, double *w,
+                          double *nrm2_dev) {
+  const int nblk = red_blocks(c, n);
+  c.red_partial.ensure((size_t)nblk);
+  maxpy_norm_kernel<<<nblk, RED_THREADS, nvec * sizeof(double), c.stream>>>(n, Vptrs_dev, nvec, h_dev, w, c.red_partial.p);
+  FNP_LAUNCH_CHECK(c);
+  reduce_partials_kernel<<<1, 128, 0, c.stream>>>(c.red_partial.p, nblk, nrm2_dev);
+  FNP_LAUNCH_CHECK(c);
+}
+
+// x += sum_i y[i] Z_i
+__global__ void __launch_bounds__(RED_THREADS)
+maxpy_kernel(int64_t n, const double *const *__restrict__ Z, int nvec, const double *__restrict__ y, double *__restrict__ x) {
+  extern __shared__ double sh[];
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) sh[i] = y[i];
+  __syncthreads();
+  GRID_STRIDE(e, n) {
+    double xv = x[e];
+    for (int i = 0; i < nvec; ++i) xv += sh[i] * __ldg(Z[i] + e);
+    x[e] = xv;
+  }
+}
+
+void multi_axpy_ptrs(Ctx &c, int64_t n, const double *const *Zptrs_dev, int nvec, const double *y_dev, double *x) {
+  if (nvec <= 0 || n <= 0) return;
+  maxpy_kernel<<<red_blocks(c, n), RED_THREADS, nvec * sizeof(double), c.stream>>>(n, Zptrs_dev, nvec, y_dev, x);
+  FNP_LAUNCH_CHECK(c);
+}
+
+__global__ void scale_inv_sqrt_kernel(int64_t n, const double *__restrict__ nrm2, const double *__restrict__ w, double *__restrict__ v) {
+  const double s = nrm2[0] > 0.0 ? 1.0 / sqrt(nrm2[0]) : 0.0;
+  GRID_STRIDE(i, n) v[i] = w[i] * s;
+}
+
+void vec_scale_inv_sqrt(Ctx &c, int64_t n, const double *nrm2_dev, const double *w, double *v) {
+  VEC_LAUNCH(scale_inv_sqrt_kernel, n, n, nrm2_dev, w, v);
+}
+
+// x = Minv b, Minv dense row-major n x n: one warp per row
+__global__ void __launch_bounds__(256)
+gemv_kernel(int n, const double *__restrict__ M, const double *__restrict__ b, double *__restrict__ x) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  double s = 0.0;
+  for (int k = lane; k < n; k += 32) s += M[(int64_t)row * n + k] * __ldg(b + k);
+  s = warp_sum(s);
+  if (lane == 0) x[row] = s;
+}
+
+void dense_gemv(Ctx &c, int n, const double *Minv, const double *b, double *x) {
+  if (n <= 0) return;
+  gemv_kernel<<<(n * 32 + 255) / 256, 256, 0, c.stream>>>(n, Minv, b, x);
+  FNP_LAUNCH_CHECK(c);
+}
+
+}  // namespace fnp

@@ -1,0 +1,197 @@
+// The PCD hot path: inner solves, the two Schur-complement approximations of
+// fenapack/preconditioners.py (PCDPC_BRM1.apply :98-135, PCDPC_BRM2.apply
+// :148-169) and the block-triangular apply of PCFIELDSPLIT SCHUR/UPPER that
+// fenapack/field_split.py:54-57 selects.  The vector updates of the reference
+// (copy, axpy, scale -- one petsc4py call each) are folded into the epilogues
+// of the neighbouring SpMV-class kernels.
+#include "fnp_internal.cuh"
+
+namespace fnp {
+
+// ---------------------------------------------------------------------------
+// CG with device-resident scalars (no host round trip per iteration)
+// ---------------------------------------------------------------------------
+__global__ void cg_xr_kernel(int64_t n, const double *__restrict__ rz, const double *__restrict__ pq,
+                             const double *__restrict__ p, const double *__restrict__ q, double *__restrict__ x,
+                             double *__restrict__ r) {
+  const double alpha = pq[0] != 0.0 ? rz[0] / pq[0] : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    r[i] -= alpha * q[i];
+  }
+}
+__global__ void cg_p_kernel(int64_t n, const double *__restrict__ rz_new, const double *__restrict__ rz_old,
+                            const double *__restrict__ z, double *__restrict__ p) {
+  const double beta = rz_old[0] != 0.0 ? rz_new[0] / rz_old[0] : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = z[i] + beta * p[i];
+}
+
+static void apply_inner_pc(Ctx &c, const InnerOpts &o, const DevCsr &A, DevHierarchy *H, const double *r, double *z) {
+  if (o.pc == PC_AMG) {
+    amg_vcycle(c, *H, r, z);
+  } else if (o.pc == PC_JACOBI) {
+    vec_pointwise_scale(c, A.nrows, 1.0, A.dinv.p, r, nullptr, z);
+  } else {
+    vec_copy(c, A.nrows, r, z);
+  }
+}
+
+// Generic inner solve  x = KSP(A, PC)(b), zero initial guess.  work: 4 vectors.
+static void inner_solve(Ctx &c, const InnerOpts &o, const DevCsr &A, DevHierarchy *H, const double *b, double *x,
+                        double *w0, double *w1, double *w2, double *w3) {
+  const int64_t n = A.nrows;
+  switch (o.ksp) {
+    case KSP_PREONLY:
+      apply_inner_pc(c, o, A, H, b, x);
+      break;
+    case KSP_RICHARDSON: {
+      // x1 = B b ; x_{k+1} = x_k + B (b - A x_k)      (KSPRICHARDSON, scale 1)
+      apply_inner_pc(c, o, A, H, b, x);
+      for (int k = 1; k < o.max_it; ++k) {
+        spmv_axpby(c, A, x, -1.0, 1.0, b, w0);
+        apply_inner_pc(c, o, A, H, w0, w1);
+        vec_axpy(c, n, 1.0, w1, x);
+      }
+      break;
+    }
+    case KSP_CHEBYSHEV:
+      FNP_REQUIRE(o.pc == PC_JACOBI, FNP_ERR_OPTION, "chebyshev is implemented with pc_type jacobi only");
+      cheb_jacobi(c, A, b, o.emin, o.emax, o.max_it, 1.0, nullptr, x, w0, w1);
+      break;
+    case KSP_CG: {
+      // preconditioned CG, fixed iteration count, scalars stay on the device
+      double *r = w0, *z = w1, *p = w2, *q = w3;
+      double *rz = c.red_out.p + 200, *rz2 = c.red_out.p + 201, *pq = c.red_out.p + 202;
+      vec_zero(c, n, x);
+      vec_copy(c, n, b, r);
+      apply_inner_pc(c, o, A, H, r, z);
+      vec_copy(c, n, z, p);
+      dot(c, n, r, z, rz);
+      const int nb = 148 * 8;
+      for (int k = 0; k < o.max_it; ++k) {
+        spmv_store(c, A, p, q);
+        dot(c, n, p, q, pq);
+        cg_xr_kernel<<<nb, 256, 0, c.stream>>>(n, rz, pq, p, q, x, r);
+        c.launches++;
+        if (k + 1 == o.max_it) break;
+        apply_inner_pc(c, o, A, H, r, z);
+        dot(c, n, r, z, rz2);
+        cg_p_kernel<<<nb, 256, 0, c.stream>>>(n, rz2, rz, z, p);
+        c.launches++;
+        std::swap(rz, rz2);
+      }
+      FNP_CUDA(cudaPeekAtLastError());
+      break;
+    }
+  }
+}
+
+void mp_solve(Ctx &c, const double *b, double out_scale, const double *add, double *x) {
+  StageTimer t(c, "FENaPack: PCD_Mp solve");
+  const DevCsr &Mp = c.dmat[FNP_MAT_MP];
+  const InnerOpts &o = c.opt_mp;
+  if (o.ksp == KSP_CHEBYSHEV && o.pc == PC_JACOBI) {
+    cheb_jacobi(c, Mp, b, o.emin, o.emax, o.max_it, out_scale, add, x, c.p_w[3].p, c.p_w[4].p);
+    return;
+  }
+  FNP_REQUIRE(add == nullptr || add != x, FNP_ERR_ARG, "mp_solve: aliasing not supported for this KSP");
+  inner_solve(c, o, Mp, nullptr, b, x, c.p_w[1].p, c.p_w[2].p, c.p_w[3].p, c.p_w[4].p);
+  if (add) vec_axpby(c, Mp.nrows, out_scale, x, 1.0, add, x);
+  else if (out_scale != 1.0) vec_scale(c, Mp.nrows, out_scale, x);
+}
+
+void ap_solve(Ctx &c, const double *b, double *x) {
+  StageTimer t(c, "FENaPack: PCD_Ap solve");
+  inner_solve(c, c.opt_ap, c.dmat[FNP_MAT_AP], &c.amg_ap, b, x, c.p_w[1].p, c.p_w[2].p, c.p_w[3].p, c.p_w[4].p);
+}
+
+void u_solve(Ctx &c, const double *b, double *x) {
+  StageTimer t(c, "FENaPack: fieldsplit_u solve");
+  inner_solve(c, c.opt_u, c.velocity_pc_matrix(), &c.amg_u, b, x, c.u_w[1].p, c.u_w[2].p, c.u_w[3].p, c.u_w[4].p);
+}
+
+void schur_apply(Ctx &c, const double *x, double *y) {
+  const int64_t n = c.n_p;
+  const DevCsr &Kp = c.dmat[FNP_MAT_KP];
+  double *z = c.p_w[0].p;
+  if (c.variant == 1) {
+    StageTimer t(c, "FENaPack: PCDPC_BRM1 apply");
+    // z = x ; z[bc] = g                        preconditioners.py:128-129
+    vec_copy_bc(c, n, x, z, c.bc_idx.p, c.bc_val.p, c.nbc);
+    // y = Ap^-1 z                              :130
+    ap_solve(c, z, y);
+    // z = Kp y + x                             :131-132
+    spmv_axpby(c, Kp, y, 1.0, 1.0, x, z);
+    // y = -Mp^-1 z                             :133-135
+    mp_solve(c, z, -1.0, nullptr, y);
+  } else {
+    StageTimer t(c, "FENaPack: PCDPC_BRM2 apply");
+    double *z0 = c.p_w[5].p;
+    // y = Mp^-1 x                              preconditioners.py:162
+    mp_solve(c, x, 1.0, nullptr, y);
+    // z = Kp y ; z[bc] = g                     :163-165
+    spmv_store(c, Kp, y, z);
+    vec_scatter_bc(c, z, c.bc_idx.p, c.bc_val.p, c.nbc);
+    // z0 = Ap^-1 z                             :166
+    ap_solve(c, z, z0);
+    // y = -(y + z0)                            :167-169
+    vec_axpby(c, n, -1.0, y, -1.0, z0, y);
+  }
+}
+
+void pc_apply(Ctx &c, const double *x_u, const double *x_p, double *y_u, double *y_p) {
+  StageTimer t(c, "FENaPack: PCD fieldsplit apply");
+  // y_p = S^-1 x_p
+  schur_apply(c, x_p, y_p);
+  // t = x_u - A01 y_p
+  double *tu = c.u_w[0].p;
+  {
+    StageTimer t2(c, "FENaPack: A01 mult");
+    spmv_axpby(c, c.dmat[FNP_MAT_A01], y_p, -1.0, 1.0, x_u, tu);
+  }
+  // y_u = A00^-1 t
+  u_solve(c, tu, y_u);
+}
+
+void system_matvec(Ctx &c, const double *x, double *y) {
+  StageTimer t(c, "FENaPack: system MatMult");
+  const double *xu = x, *xp = x + c.n_u;
+  double *yu = y, *yp = y + c.n_u;
+  spmv_store(c, c.dmat[FNP_MAT_A00], xu, yu);
+  spmv_axpby(c, c.dmat[FNP_MAT_A01], xp, 1.0, 1.0, yu, yu);
+  spmv_store(c, c.dmat[FNP_MAT_A10], xu, yp);
+}
+
+// ---------------------------------------------------------------------------
+// set-up
+// ---------------------------------------------------------------------------
+static void build_amg(Ctx &c, int which, DevHierarchy &H, const AmgParams &p) {
+  H.params = p;
+  amg_build_host(c.hmat[which], p, H.host);
+  amg_upload(c, H);
+}
+
+void setup_all(Ctx &c) {
+  StageTimer t(c, "FENaPack: setup");
+  FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must be called before fnp_setup");
+  const int required[] = {FNP_MAT_A00, FNP_MAT_A01, FNP_MAT_A10, FNP_MAT_AP, FNP_MAT_MP, FNP_MAT_KP};
+  for (int w : required)
+    FNP_REQUIRE(c.have_values[w], FNP_ERR_STATE, "fnp_setup: operator " + std::to_string(w) + " has no values");
+  FNP_REQUIRE(c.variant == 1 || c.variant == 2, FNP_ERR_STATE, "PCD variant not set");
+  for (auto &b : c.p_w) b.ensure((size_t)c.n_p);
+  for (auto &b : c.u_w) b.ensure((size_t)c.n_u);
+  c.red_out.ensure(256);
+  // Jacobi diagonals
+  const int uidx = c.velocity_pc_index();
+  for (int w : {(int)FNP_MAT_MP, (int)FNP_MAT_AP, uidx})
+    if (c.dirty[w] || !c.dmat[w].has_dinv) extract_diag_inv(c, c.dmat[w]);
+  // AMG hierarchies (Ap: once; velocity block: whenever its values changed)
+  if (c.opt_ap.pc == PC_AMG && (c.dirty[FNP_MAT_AP] || !c.amg_ap.built)) build_amg(c, FNP_MAT_AP, c.amg_ap, c.opt_ap.amg);
+  if (c.opt_u.pc == PC_AMG && (c.dirty[uidx] || !c.amg_u.built)) build_amg(c, uidx, c.amg_u, c.opt_u.amg);
+  for (int w = 0; w < FNP_MAT_COUNT; ++w) c.dirty[w] = false;
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  c.is_setup = true;
+}
+
+}  // namespace fnp

@@ -1,0 +1,185 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on
+the same seeded inputs.  Tolerances are BASELINE.json's: SpMV and the
+fixed-iteration Chebyshev-Jacobi apply <= 1e-12 relative, full PC apply <= 1e-8
+relative, outer FGMRES iteration counts within +-1 at the same final residual."""
+import numpy as np
+import pytest
+
+from fenapack_b200 import capi
+from oracle import amg as oamg
+from oracle import petsc_algos as pa
+from oracle import problems
+
+from util import make_context, oracle_hierarchy_from_device, oracle_preconditioner, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_SPMV = 1e-12
+TOL_PC = 1e-8
+
+
+@pytest.fixture(scope="module", params=["bfs_BRM1", "bfs_BRM2", "cavity3d_BRM2", "channel3d_BRM1"])
+def case(request):
+    name = request.param
+    if name.startswith("bfs"):
+        variant = name.split("_")[1]
+        # a Picard step around a non-trivial wind (the Stokes solution)
+        p0, space = problems.backward_facing_step(3, variant=variant)
+        x = pa.direct_solver(p0.system_matrix())(p0.rhs())
+        prob, _ = problems.backward_facing_step(3, variant=variant, wind=x[:p0.n_u].reshape(-1, 2))
+    elif name.startswith("cavity3d"):
+        prob, _ = problems.lid_driven_cavity(8, dim=3, variant="BRM2")
+    else:
+        prob, _ = problems.channel(12, 4, 4, variant="BRM1")
+    ctx = make_context(prob)
+    yield prob, ctx
+    ctx.close()
+
+
+def test_spmv_all_operators(case):
+    prob, ctx = case
+    rng = np.random.default_rng(0)
+    mats = {capi.MAT_A00: prob.A00, capi.MAT_A01: prob.A01, capi.MAT_A10: prob.A10,
+            capi.MAT_AP: prob.Ap, capi.MAT_MP: prob.Mp, capi.MAT_KP: prob.Kp}
+    for which, A in mats.items():
+        x = rng.standard_normal(A.shape[1])
+        y = ctx.spmv(which, x, A.shape[0])
+        assert relerr(y, A @ x) <= TOL_SPMV, which
+
+
+def test_chebyshev_jacobi_mp(case):
+    prob, ctx = case
+    b = np.random.default_rng(1).standard_normal(prob.n_p)
+    dinv = 1.0 / prob.Mp.diagonal()
+    ref = pa.chebyshev_jacobi(prob.Mp, dinv, b, *prob.cheb_bounds, 5)
+    assert relerr(ctx.mp_solve(b), ref) <= TOL_SPMV
+    # and it is a decent approximation of Mp^-1 (degree-5 Chebyshev: error factor <= ~1e-2)
+    exact = pa.direct_solver(prob.Mp)(b)
+    assert relerr(ref, exact) < 5e-2
+
+
+def test_amg_hierarchy_matches_oracle_setup(case):
+    prob, ctx = case
+    for which, A in ((capi.MAT_AP, prob.Ap), (capi.MAT_A00, prob.P00 if prob.P00 is not None else prob.A00)):
+        levels, cinv = ctx.amg_hierarchy(which)
+        H = oamg.build_hierarchy(A)
+        assert [l["A"].shape[0] for l in levels] == [l.A.shape[0] for l in H.levels]
+        for dl, ol in zip(levels, H.levels):
+            assert abs(dl["rho"] - ol.rho) <= 1e-10 * ol.rho
+            d = (dl["A"] - ol.A)
+            assert abs(d).max() <= 1e-10 * abs(ol.A).max()
+            if ol.P is not None:
+                assert abs(dl["P"] - ol.P).max() <= 1e-10
+        assert np.abs(cinv - H.coarse_inv).max() <= 1e-8 * np.abs(H.coarse_inv).max()
+
+
+def test_amg_vcycle(case):
+    prob, ctx = case
+    rng = np.random.default_rng(2)
+    for which, n in ((capi.MAT_AP, prob.n_p), (capi.MAT_A00, prob.n_u)):
+        H = oracle_hierarchy_from_device(ctx, which)
+        b = rng.standard_normal(n)
+        assert relerr(ctx.amg_vcycle(which, b), H.vcycle(b)) <= 1e-11
+
+
+def test_inner_solves(case):
+    prob, ctx = case
+    pc = oracle_preconditioner(prob, ctx)
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(prob.n_p)
+    assert relerr(ctx.ap_solve(b), pc.solve_Ap(b)) <= 1e-11
+    b = rng.standard_normal(prob.n_u)
+    assert relerr(ctx.u_solve(b), pc.solve_A00(b)) <= 1e-11
+
+
+def test_schur_apply(case):
+    prob, ctx = case
+    pc = oracle_preconditioner(prob, ctx)
+    x = np.random.default_rng(4).standard_normal(prob.n_p)
+    x0 = x.copy()
+    y = ctx.schur_apply(x)
+    assert np.array_equal(x, x0)          # apply must not modify x
+    assert relerr(y, pc.schur_apply(x)) <= TOL_PC
+
+
+def test_pc_apply(case):
+    prob, ctx = case
+    pc = oracle_preconditioner(prob, ctx)
+    rng = np.random.default_rng(5)
+    xu, xp = rng.standard_normal(prob.n_u), rng.standard_normal(prob.n_p)
+    yu, yp = ctx.pc_apply(xu, xp)
+    ru, rp = pc.apply_split(xu, xp)
+    assert relerr(yp, rp) <= TOL_PC
+    assert relerr(yu, ru) <= TOL_PC
+
+
+@pytest.mark.parametrize("ksp_type", ["fgmres", "gmres"])
+def test_outer_solve_iteration_parity(case, ksp_type):
+    prob, ctx = case
+    ctx.set_option("ksp_type", ksp_type)
+    pc = oracle_preconditioner(prob, ctx)
+    A, b = prob.system_matrix(), prob.rhs()
+    x_ref, its_ref, hist_ref, nap_ref = pa.fgmres(A, pc, b, rtol=1e-6, restart=150, flexible=(ksp_type == "fgmres"))
+    xu, xp, its, rn, nap = ctx.solve(prob.b_u, prob.b_p)
+    assert abs(its - its_ref) <= 1
+    assert nap == its + (0 if ksp_type == "fgmres" else 1)
+    x = np.concatenate([xu, xp])
+    true_res = np.linalg.norm(b - A @ x) / np.linalg.norm(b)
+    assert true_res <= 2e-6
+    hist = ctx.residual_history()
+    k = min(len(hist), len(hist_ref)) - 1
+    assert np.allclose(hist[:k], hist_ref[:k], rtol=1e-5)
+    if its == its_ref:
+        assert relerr(x, x_ref) <= 1e-6
+    ctx.set_option("ksp_type", "fgmres")
+
+
+def test_monolithic_solve_permutation(case):
+    prob, ctx = case
+    n = prob.n_u + prob.n_p
+    b = np.empty(n)
+    b[prob.is_u] = prob.b_u
+    b[prob.is_p] = prob.b_p
+    x, its, rn, nap = ctx.solve_monolithic(b)
+    xu, xp, its2, _, _ = ctx.solve(prob.b_u, prob.b_p)
+    assert its == its2
+    assert np.array_equal(x[prob.is_u], xu) and np.array_equal(x[prob.is_p], xp)
+
+
+def test_value_refresh_same_pattern():
+    """Per-Newton-step refresh: same pattern, new Kp / A00 values."""
+    p0, space = problems.backward_facing_step(2, variant="BRM1")
+    ctx = make_context(p0)
+    x = pa.direct_solver(p0.system_matrix())(p0.rhs())
+    p1, _ = problems.backward_facing_step(2, variant="BRM1", wind=x[:p0.n_u].reshape(-1, 2))
+    assert np.array_equal(p1.A00.indices, p0.A00.indices) and np.array_equal(p1.Kp.indptr, p0.Kp.indptr)
+    ctx.set_values(capi.MAT_A00, p1.A00.data)
+    ctx.set_values(capi.MAT_KP, p1.Kp.data)
+    ctx.setup()
+    pc = oracle_preconditioner(p1, ctx)
+    rng = np.random.default_rng(7)
+    xu, xp = rng.standard_normal(p1.n_u), rng.standard_normal(p1.n_p)
+    yu, yp = ctx.pc_apply(xu, xp)
+    ru, rp = pc.apply_split(xu, xp)
+    assert relerr(yp, rp) <= TOL_PC and relerr(yu, ru) <= TOL_PC
+    with pytest.raises(ValueError):
+        ctx.set_values(capi.MAT_KP, p1.Kp.data[:-1])
+    ctx.close()
+
+
+def test_error_conventions():
+    ctx = capi.Context(0)
+    with pytest.raises(capi.FenapackCudaError) as e:
+        ctx.set_option("fieldsplit_p_PCD_Mp_ksp_type", "bogus")
+    assert e.value.code == capi.ERR_OPTION
+    with pytest.raises(capi.FenapackCudaError) as e:
+        ctx.set_option("no_such_option", "1")
+    assert e.value.code == capi.ERR_OPTION
+    with pytest.raises(capi.FenapackCudaError) as e:
+        ctx.setup()
+    assert e.value.code == capi.ERR_STATE
+    ctx.set_layout(10, 4)
+    with pytest.raises(capi.FenapackCudaError) as e:
+        ctx.set_layout(10, 4)      # re-initialisation is rejected (field_split.py:60)
+    assert e.value.code == capi.ERR_STATE
+    ctx.close()
