@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py -- PCD PC applies/s and FGMRES time-to-solve, 3D P2/P1 Oseen, N B200.
+
+One "step" = one right-preconditioned FGMRES(150) solve (rtol 1e-6) of the 3D
+P2/P1 Oseen system with the block-triangular PCD preconditioner (inner solvers:
+the reference's "iterative" set-up, demo_navier-stokes-pcd.py:153-165, with the
+SA-AMG V-cycle in BoomerAMG's slot).  `value` = PC applies per second inside
+those solves (device-resident vectors), `ms_per_step` = time to solution,
+`e2e` = the same through the C-ABI call with HOST vectors (copies inside).
+
+Workload family (config.workload): lid-driven cavity on the unit cube,
+n x n x n bricks x 6 tetrahedra, P2/P1, nu = 0.02, Oseen wind = analytic
+recirculation, PCD BRM2.  Weak scaling: n = round(n1 * N^(1/3)), rows of all
+operators partitioned over the N GPUs in contiguous z-slabs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n1 64] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPTIONS = {
+    "ksp_type": "fgmres",
+    "ksp_gmres_restart": 150,
+    "ksp_rtol": 1e-6,
+    "fieldsplit_u_ksp_type": "richardson",
+    "fieldsplit_u_ksp_max_it": 1,
+    "fieldsplit_u_pc_type": "hypre",
+    "fieldsplit_u_pc_hypre_type": "boomeramg",
+    "fieldsplit_p_PCD_Ap_ksp_type": "richardson",
+    "fieldsplit_p_PCD_Ap_ksp_max_it": 2,
+    "fieldsplit_p_PCD_Ap_pc_type": "hypre",
+    "fieldsplit_p_PCD_Ap_pc_hypre_type": "boomeramg",
+    "fieldsplit_p_PCD_Mp_ksp_type": "chebyshev",
+    "fieldsplit_p_PCD_Mp_ksp_max_it": 5,
+    "fieldsplit_p_PCD_Mp_ksp_chebyshev_eigenvalues": "0.5, 2.5",
+    "fieldsplit_p_PCD_Mp_pc_type": "jacobi",
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cavity3d", choices=["cavity3d", "channel3d"])
+    ap.add_argument("--n1", type=int, default=64, help="bricks per side on one GPU (weak scaling base)")
+    ap.add_argument("--variant", default=None, choices=["BRM1", "BRM2"])
+    ap.add_argument("--nu", type=float, default=0.02)
+    ap.add_argument("--cpu-sample-its", type=int, default=12,
+                    help="FGMRES iterations of the same solve timed on the host cores")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="skip e2e/cpu legs (for ncu runs)")
+    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
+    return ap.parse_args()
+
+
+def mesh_size(args, world):
+    n = int(round(args.n1 * world ** (1.0 / 3.0)))
+    if args.workload == "cavity3d":
+        return (n, n, n), "cavity", args.variant or "BRM2"
+    m = max(2, int(round(n / 4.0 ** (1.0 / 3.0))))      # 4m x m x m bricks of the 4x1x1 box: ~n^3 bricks
+    return (4 * m, m, m), "channel", args.variant or "BRM1"
+
+
+def workload_name(args, dims, kind, variant, ndofs):
+    return (f"{'lid-driven cavity' if kind == 'cavity' else 'channel'} 3D P2/P1 Oseen, {dims[0]}x{dims[1]}x{dims[2]} bricks x6 tets, "
+            f"{ndofs} dofs, nu={args.nu}, PCD {variant}, FGMRES(150) rtol 1e-6, "
+            "u: richardson x1 + SA-AMG V(2,2) Chebyshev-Jacobi, Ap: richardson x2 + SA-AMG, Mp: chebyshev x5 + jacobi")
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        self.idx = gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        try:
+            self.f.flush()
+            rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            if sm:
+                out["samples"] = len(sm)
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["power_w_max"] = max(float(r[3]) for r in rows if len(r) >= 9)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for k, nm in enumerate(names):
+                    if any(r[5 + k].strip().lower().startswith("active") for r in rows if len(r) >= 9):
+                        out["reasons"].append(nm)
+        except Exception as e:  # pragma: no cover
+            out["error"] = str(e)
+        finally:
+            try:
+                os.unlink(self.f.name)
+            except OSError:
+                pass
+        return out
+
+
+class NoClocks:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+    def summary(self):
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def spmv_bytes(nrows, ncols, nnz):
+    # matrix once (8 B value + 4 B column), row pointers, y written once, x read once
+    return 12.0 * nnz + 4.0 * (nrows + 1) + 8.0 * nrows + 8.0 * ncols
+
+
+# ---------------------------------------------------------------------------
+# CPU arm (oracle port, C/OpenMP): the reference's algorithm chain on the host cores
+# ---------------------------------------------------------------------------
+def cpu_port_sample(prob, hier_u, hier_p, variant, its, rtol=1e-6):
+    """Time the first `its` FGMRES iterations of the same solve with the
+    C/OpenMP restatement (oracle/pcd_ref.c).  Returns (applies/s, seconds, its, threads)."""
+    from oracle import cref
+    mats = {k: prob.scipy(k) for k in ("A00", "A01", "A10", "Ap", "Mp", "Kp")}
+    pc = cref.CPCD(mats, variant, prob.bc_idx, prob.bc_val, hier_u, hier_p, prob.cheb_bounds)
+    b = np.concatenate([prob.b_u, prob.b_p])
+    pc.fgmres(b, rtol=rtol, restart=150, max_it=1)          # warm-up (page in, thread pool)
+    t0 = time.perf_counter()
+    x, n_it, hist, nap = pc.fgmres(b, rtol=rtol, restart=150, max_it=its)
+    dt = time.perf_counter() - t0
+    return nap / dt, dt, n_it, cref.num_threads(), hist
+
+
+def oracle_hierarchies_from_library(ctx):
+    """The hierarchies the GPU library built, as oracle objects (same inner operators
+    on both sides)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fenapack_b200 import capi
+    from util import oracle_hierarchy_from_device
+    return oracle_hierarchy_from_device(ctx, capi.MAT_A00), oracle_hierarchy_from_device(ctx, capi.MAT_AP)
+
+
+# ---------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from fenapack_b200 import capi
+    import bench_inputs as bi
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dims, kind, variant = mesh_size(args, world)
+
+    t0 = time.perf_counter()
+    prob = bi.OseenBoxProblem(*dims, kind=kind, nu=args.nu, variant=variant, rank=rank, nranks=world,
+                              device=f"cuda:{local}")
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    t_gen = time.perf_counter() - t0
+
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx = capi.Context(local, nccl_id=bytes(idt.cpu().numpy().tobytes()), rank=rank, nranks=world)
+    else:
+        ctx = capi.Context(local)
+    opts = dict(OPTIONS)
+    opts["fieldsplit_p_pc_python_type"] = "fenapack.PCDPC_" + variant
+    ctx.set_options(opts)
+    t0 = time.perf_counter()
+    ctx.set_layout(prob.n_u, prob.n_p, prob.u_begin, prob.n_u_global, prob.p_begin, prob.n_p_global)
+    for name, which in (("A00", capi.MAT_A00), ("A01", capi.MAT_A01), ("A10", capi.MAT_A10),
+                        ("Ap", capi.MAT_AP), ("Mp", capi.MAT_MP), ("Kp", capi.MAT_KP)):
+        rp, ci, va = getattr(prob, name)
+        ctx.set_pattern(which, rp, ci)
+        ctx.set_values(which, va)
+    ctx.set_bc(prob.bc_idx, prob.bc_val)
+    t_upload = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ctx.setup()
+    t_setup = time.perf_counter() - t0
+
+    n_loc = prob.n_u + prob.n_p
+    # device-resident right-hand side / solution (torch is only the allocator here)
+    b_dev = torch.from_numpy(np.concatenate([prob.b_u, prob.b_p])).cuda()
+    x_dev = torch.empty_like(b_dev)
+    bu_p, bp_p = b_dev.data_ptr(), b_dev.data_ptr() + 8 * prob.n_u
+    xu_p, xp_p = x_dev.data_ptr(), x_dev.data_ptr() + 8 * prob.n_u
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up -------------------------------------------------------------
+    nwarm = args.warmup if args.profile_only else max(args.warmup, 3)
+    for _ in range(nwarm):
+        its, rn, nap = ctx.solve_device(bu_p, bp_p, xu_p, xp_p)
+    # ---- timed region: K solves, CUDA events on the library's stream ----------
+    with (ClockSampler(local) if not args.no_clocks else NoClocks()) as clk:
+        barrier()
+        l0 = ctx.kernel_launches()
+        ctx.tic()
+        total_applies = 0
+        for _ in range(args.steps):
+            its, rn, nap = ctx.solve_device(bu_p, bp_p, xu_p, xp_p)
+            total_applies += nap
+        ms = ctx.toc()
+        barrier()
+        launches = ctx.kernel_launches() - l0
+    clocks = clk.summary()
+    ms = max_over_ranks(ms)
+    value = total_applies / (ms * 1e-3)
+    hist = ctx.residual_history()
+    final_rel = float(hist[-1] / hist[0])
+
+    result = {
+        "metric": "pcd_pc_applies_per_s", "value": value, "unit": "PC applies/s", "n_gpus": world,
+        "steps": args.steps, "warmup": nwarm, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, dims, kind, variant, prob.ndofs_global),
+                   "ndofs": prob.ndofs_global, "n_u": prob.n_u_global, "n_p": prob.n_p_global,
+                   "partition": f"row slabs x{world}", "l2": "inputs larger than L2 (A00 alone >> 126 MB), no flush"},
+        "time_to_solve_ms": ms / args.steps, "fgmres_iterations": its, "pc_applies_per_solve": nap,
+        "final_rel_residual": final_rel, "clocks": clocks, "gpu_launches": int(launches),
+        "setup": {"generate_s": t_gen, "upload_s": t_upload, "fnp_setup_s": t_setup},
+    }
+
+    if not args.profile_only:
+        # ---- e2e: the C-ABI call with HOST (pinned) vectors, copies inside the timed region ----
+        bu_h = torch.from_numpy(prob.b_u.copy()).pin_memory().numpy()
+        bp_h = torch.from_numpy(prob.b_p.copy()).pin_memory().numpy()
+        ctx.solve(bu_h, bp_h)
+        barrier()
+        t0 = time.perf_counter()
+        applies = 0
+        for _ in range(args.steps):
+            xu, xp, its_h, rn_h, nap_h = ctx.solve(bu_h, bp_h)
+            applies += nap_h
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        hess = sum(8 * (j + 2) for j in range(its_h)) + 16
+        result["e2e"] = {"value": applies / dt, "unit": "PC applies/s", "ms_per_solve": 1e3 * dt / args.steps,
+                         "h2d_bytes_per_step": 8 * n_loc, "d2h_bytes_per_step": 8 * n_loc + hess,
+                         "api": "fnp_solve(host pointers)"}
+        # standalone PC applies on device-resident vectors
+        z_dev = torch.empty_like(b_dev)
+        zu_p, zp_p = z_dev.data_ptr(), z_dev.data_ptr() + 8 * prob.n_u
+        for _ in range(3):
+            ctx.pc_apply_device(bu_p, bp_p, zu_p, zp_p)
+        barrier()
+        ctx.tic()
+        reps = 20
+        for _ in range(reps):
+            ctx.pc_apply_device(bu_p, bp_p, zu_p, zp_p)
+        pms = max_over_ranks(ctx.toc())
+        result["pc_apply_only"] = {"applies_per_s": reps / (pms * 1e-3), "ms_per_apply": pms / reps}
+
+    # ---- roofline of the dominant kernel, measured in situ (instrumented solve) ----------
+    ctx.set_option("fnp_timers", 2)
+    ctx.reset_timers()
+    ctx.solve_device(bu_p, bp_p, xu_p, xp_p)
+    stage = {}
+    for nm in ("FENaPack: PCDKSP solve", "FENaPack: PCD fieldsplit apply", "FENaPack: PCDPC_%s apply" % variant,
+               "FENaPack: PCD_Ap solve", "FENaPack: PCD_Mp solve", "FENaPack: fieldsplit_u solve",
+               "FENaPack: A01 mult", "FENaPack: system MatMult", "spmv A00", "spmv A01", "spmv A10", "spmv Ap",
+               "spmv Mp", "spmv Kp", "spmv A00/L1", "spmv A00/P0", "spmv A00/R0", "FENaPack: GMRES orthogonalization"):
+        t_ms, calls = ctx.timer(nm)
+        if calls:
+            stage[nm] = {"ms": t_ms, "calls": calls}
+    ctx.set_option("fnp_timers", 0)
+    peak, peak_src = hbm_peak()
+    rpA, ciA, vaA = prob.A00
+    bytes_a00 = spmv_bytes(prob.n_u, prob.n_u, int(rpA[-1]))      # local rows; ghosts are a few planes
+    roof = {"bound": "hbm", "kernel": "spmv_kernel<LANES,Epi> on A00 (P2 velocity block, AMG level 0 + outer MatMult)",
+            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "bytes_per_launch": bytes_a00}
+    if "spmv A00" in stage:
+        avg_ms = stage["spmv A00"]["ms"] / stage["spmv A00"]["calls"]
+        roof["avg_launch_ms"] = avg_ms
+        roof["achieved"] = bytes_a00 / (avg_ms * 1e-3) / 1e9
+        roof["frac"] = roof["achieved"] / peak
+        tot = stage.get("FENaPack: PCDKSP solve", {}).get("ms")
+        if tot:
+            roof["share_of_step"] = stage["spmv A00"]["ms"] / tot
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    roof["traffic"] = None
+    if os.path.exists(tpath):
+        try:
+            roof["traffic"] = json.load(open(tpath)).get("spmv_A00_dram_bytes_per_launch")
+        except Exception:
+            pass
+    result["roofline"] = roof
+    result["stages"] = stage
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample ----
+    if world == 1 and not args.no_cpu_baseline and not args.profile_only:
+        try:
+            Hu, Hp = oracle_hierarchies_from_library(ctx)
+            v, dt, n_it, thr, chist = cpu_port_sample(prob, Hu, Hp, variant, args.cpu_sample_its)
+            k = min(len(chist), len(hist)) - 1
+            result["cpu_baseline"] = {
+                "value": v, "unit": "PC applies/s", "cores": thr, "kind": "port",
+                "sample": f"first {n_it} FGMRES iterations of the same solve ({dt:.1f} s), C/OpenMP restatement "
+                          "oracle/pcd_ref.c on the AMG hierarchy the library built",
+                "host_cpus": os.cpu_count(),
+                "residual_after_sample_rel_diff_vs_gpu": float(abs(chist[k] - hist[k]) / hist[k]),
+            }
+        except Exception as e:  # keep the bench line even if the host leg fails
+            result["cpu_baseline"] = {"value": None, "unit": "PC applies/s", "cores": 0, "kind": "port",
+                                      "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(result))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------
+# reference arm: the reference's algorithm chain on the host cores (oracle port)
+# ---------------------------------------------------------------------------
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    import torch
+    import bench_inputs as bi
+    from oracle import amg as oamg
+    from oracle import cref
+    dims, kind, variant = mesh_size(args, world)
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    prob = bi.OseenBoxProblem(*dims, kind=kind, nu=args.nu, variant=variant, device=dev)
+    t0 = time.perf_counter()
+    Hu = oamg.build_hierarchy(prob.scipy("A00"))
+    Hp = oamg.build_hierarchy(prob.scipy("Ap"))
+    t_setup = time.perf_counter() - t0
+    mats = {k: prob.scipy(k) for k in ("A00", "A01", "A10", "Ap", "Mp", "Kp")}
+    pc = cref.CPCD(mats, variant, prob.bc_idx, prob.bc_val, Hu, Hp, prob.cheb_bounds)
+    b = np.concatenate([prob.b_u, prob.b_p])
+    its = max(2, min(args.cpu_sample_its, 6))
+    for _ in range(max(1, min(args.warmup, 1))):
+        pc.fgmres(b, rtol=1e-6, restart=150, max_it=1)
+    t0 = time.perf_counter()
+    applies = 0
+    for _ in range(args.steps):
+        _, n_it, hist, nap = pc.fgmres(b, rtol=1e-6, restart=150, max_it=its)
+        applies += nap
+    dt = time.perf_counter() - t0
+    v = applies / dt
+    thr = cref.num_threads()
+    sample = (f"each step = first {its} FGMRES iterations of the same solve; C/OpenMP restatement "
+              f"(oracle/pcd_ref.c) of the PETSc algorithm chain, {thr} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "pcd_pc_applies_per_s", "value": v, "unit": "PC applies/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, dims, kind, variant, prob.ndofs_global),
+                   "ndofs": prob.ndofs_global},
+        "cpu_baseline": {"value": v, "unit": "PC applies/s", "cores": thr, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "PC applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "setup": {"oracle_amg_setup_s": t_setup},
+        "note": "the reference itself (petsc4py/DOLFIN/hypre) is not installable in this image; see DESIGN.md",
+    }))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        b200_arm(a)

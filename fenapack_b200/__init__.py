@@ -12,3 +12,8 @@ P2/P1 Oseen / Navier-Stokes system.
 The CUDA library is mandatory; nothing here falls back to the CPU.
 """
 __version__ = "0.1.0"
+
+from .assembling import PCDAssembler, PCDForm  # noqa: E402,F401
+from .field_split import PCDKSP, PCDKrylovSolver  # noqa: E402,F401
+from .nonlinear_solvers import PCDNewtonSolver, PCDNonlinearProblem  # noqa: E402,F401
+from .preconditioners import PCDPC_BRM1, PCDPC_BRM2, PCDRPC_BRM1, PCDRPC_BRM2  # noqa: E402,F401

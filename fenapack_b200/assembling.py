@@ -1,0 +1,156 @@
+"""Form bookkeeping of the PCD preconditioner -- drop-in for fenapack/assembling.py.
+
+Assembly stays on the host (BASELINE.json north_star).  With DOLFIN the
+``a, L, mp, ap, kp ...`` arguments are UFL forms and the work is delegated to
+``dolfin.SystemAssembler`` / ``dolfin.assemble`` exactly as the reference does
+(assembling.py:85-180).  Without DOLFIN (this image) every "form" is a *host
+assembler callable* ``form() -> scipy.sparse matrix`` (or vector) on the full
+mixed space in monolithic numbering, and a boundary condition is any object with
+``dofs()`` (monolithic indices) and ``values()``.  Either way the contract seen
+by PCDInterface is the same: tensors on the mixed space W.
+
+BC semantics kept from the reference: ``ap`` gets ``bcs_pcd`` applied
+symmetrically (assembling.py:151-155); ``mp, mu, fp, kp`` get none (:158-171);
+``gp`` gets the velocity BCs (:174-180).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+try:  # pragma: no cover
+    import dolfin  # type: ignore
+    HAVE_DOLFIN = True
+except Exception:
+    dolfin = None
+    HAVE_DOLFIN = False
+
+
+class PCDForm(object):
+    """Wrapper of a PCD operator form with the two flags of the reference
+    (assembling.py:201-230): ``const`` (assemble once) and ``phantom`` (not
+    assembled, taken from the system matrix instead)."""
+
+    def __init__(self, form, const=False, phantom=False):
+        assert isinstance(const, bool) and isinstance(phantom, bool)
+        self._form = form
+        self._const = const
+        self._phantom = phantom
+
+    @property
+    def ufl(self):
+        return self._form
+
+    form = ufl
+
+    def is_constant(self):
+        return self._const
+
+    def constant(self, value=True):
+        self._const = bool(value)
+        return self
+
+    def is_phantom(self):
+        return self._phantom
+
+    def phantom(self, value=True):
+        self._phantom = bool(value)
+        return self
+
+
+def _symmetric_dirichlet(A, dofs):
+    """Rows and columns of ``dofs`` zeroed, unit diagonal (what
+    ``SystemAssembler`` does to the matrix); the pattern is kept."""
+    A = sp.csr_matrix(A, copy=True)
+    mask = np.zeros(A.shape[0], dtype=bool)
+    mask[dofs] = True
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    kill = mask[rows] | mask[A.indices]
+    A.data[kill] = 0.0
+    A.data[kill & (rows == A.indices)] = 1.0
+    return A
+
+
+class PCDAssembler(object):
+    """Collects the forms of the system and of the PCD operators and assembles
+    them on demand.  Signature and defaults as the reference (assembling.py:35-37,
+    98-106): ``ap, mp, mu, gp`` constant, ``fp, kp`` not, ``gp`` phantom."""
+
+    def __init__(self, a, L, bcs, a_pc=None, mp=None, mu=None, ap=None, fp=None, kp=None, gp=None,
+                 bcs_pcd=[], function_space=None):
+        self._a, self._L, self._a_pc = a, L, a_pc
+        self._bcs = list(bcs) if isinstance(bcs, (list, tuple)) else [bcs]
+        self._bcs_pcd = list(bcs_pcd) if isinstance(bcs_pcd, (list, tuple)) else [bcs_pcd]
+        self._W = function_space
+        self._forms = {
+            "ap": PCDForm(ap, const=True), "mp": PCDForm(mp, const=True), "mu": PCDForm(mu, const=True),
+            "fp": PCDForm(fp), "kp": PCDForm(kp), "gp": PCDForm(gp, const=True, phantom=True),
+        }
+        # user may pass ready-made PCDForm instances to override the flags
+        for key, f in (("ap", ap), ("mp", mp), ("mu", mu), ("fp", fp), ("kp", kp), ("gp", gp)):
+            if isinstance(f, PCDForm):
+                self._forms[key] = f
+        if HAVE_DOLFIN and function_space is None and hasattr(a, "arguments"):  # pragma: no cover
+            self._W = a.arguments()[0].function_space()
+            self._assembler = dolfin.SystemAssembler(a, L, self._bcs)
+            self._assembler_pc = dolfin.SystemAssembler(a_pc, L, self._bcs) if a_pc is not None else None
+
+    # -- accessors -----------------------------------------------------------
+    def function_space(self):
+        return self._W
+
+    def get_pcd_form(self, key):
+        form = self._forms[key]
+        if form.ufl is None:
+            raise AttributeError("Form '%s' requested by PCD not available" % key)
+        return form
+
+    def get_dolfin_form(self, key):
+        return self.get_pcd_form(key).ufl
+
+    def pcd_bcs(self):
+        if not self._bcs_pcd:
+            raise AttributeError("BCs requested by PCD not available")
+        return self._bcs_pcd
+
+    def bcs(self):
+        return self._bcs
+
+    # -- system --------------------------------------------------------------
+    def _assemble(self, form):
+        out = form() if callable(form) else form
+        return out
+
+    def system_matrix(self, A):
+        A.set_csr(self._assemble(self._a))
+
+    def rhs_vector(self, b, x=None):
+        b.array[:] = self._assemble(self._L)
+
+    def pc_matrix(self, P):
+        if self._a_pc is None:
+            return None
+        P.set_csr(self._assemble(self._a_pc))
+        return P
+
+    # -- PCD operators on the mixed space --------------------------------------
+    def ap(self, Ap):
+        A = self._assemble(self.get_dolfin_form("ap"))
+        dofs = np.concatenate([np.asarray(bc.dofs(), dtype=np.int64) for bc in self.pcd_bcs()]) \
+            if self._bcs_pcd else np.zeros(0, dtype=np.int64)
+        Ap.set_csr(_symmetric_dirichlet(A, dofs))
+
+    def mp(self, Mp):
+        Mp.set_csr(self._assemble(self.get_dolfin_form("mp")))
+
+    def mu(self, Mu):
+        Mu.set_csr(self._assemble(self.get_dolfin_form("mu")))
+
+    def fp(self, Fp):
+        Fp.set_csr(self._assemble(self.get_dolfin_form("fp")))
+
+    def kp(self, Kp):
+        Kp.set_csr(self._assemble(self.get_dolfin_form("kp")))
+
+    def gp(self, Bt):
+        Bt.set_csr(self._assemble(self.get_dolfin_form("gp")))

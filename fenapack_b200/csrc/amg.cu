@@ -57,34 +57,31 @@ void cheb_jacobi(Ctx &c, const DevCsr &A, const double *b, double emin, double e
   }
 }
 
-static void upload_csr(Ctx &c, const HostCsr &h, DevCsr &d) {
-  d.nrows = (int32_t)h.nrows;
-  d.ncols_own = (int32_t)h.ncols;
-  d.nghost = 0;
-  d.nnz = h.nnz();
-  d.rowptr.upload(h.rowptr.data(), h.rowptr.size(), c.stream);
-  d.col.upload(h.col.data(), h.col.size(), c.stream);
-  d.val.upload(h.val.data(), h.val.size(), c.stream);
-  d.mean_row = h.nrows ? (double)d.nnz / (double)h.nrows : 0.0;
-  int lanes = 2;
-  while (lanes < 32 && lanes * 2 < d.mean_row + 0.5) lanes *= 2;
-  d.lanes = lanes;
+static void upload_csr(Ctx &c, const HostCsr &h, DevCsr &d, const std::string &tag) {
+  csr_upload_pattern(c, d, h, tag);
+  csr_set_values(c, d, h, h.val.data(), false);
 }
 
-void amg_upload(Ctx &c, DevHierarchy &H) {
+void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0) {
   const size_t L = H.host.levels.size();
   H.levels.clear();
   H.levels.resize(L);
   for (size_t l = 0; l < L; ++l) {
     const HostLevel &hl = H.host.levels[l];
     DevLevel &dl = H.levels[l];
-    upload_csr(c, hl.A, dl.A);
-    dl.A.dinv.upload(hl.dinv.data(), hl.dinv.size(), c.stream);
-    dl.A.has_dinv = true;
+    if (l == 0 && level0) {
+      dl.Ap = level0;
+      FNP_REQUIRE(level0->has_dinv && level0->nrows == hl.A.nrows, FNP_ERR_STATE, "AMG level 0 operator mismatch");
+    } else {
+      dl.Ap = &dl.A_own;
+      upload_csr(c, hl.A, dl.A_own, name + "/L" + std::to_string(l));
+      dl.A_own.dinv.upload(hl.dinv.data(), hl.dinv.size(), c.stream);
+      dl.A_own.has_dinv = true;
+    }
     dl.rho = hl.rho;
     if (l + 1 < L) {
-      upload_csr(c, hl.P, dl.P);
-      upload_csr(c, hl.R, dl.R);
+      upload_csr(c, hl.P, dl.P, name + "/P" + std::to_string(l));
+      upload_csr(c, hl.R, dl.R, name + "/R" + std::to_string(l));
     }
     const size_t n = (size_t)hl.A.nrows;
     dl.x.alloc(n); dl.b.alloc(n); dl.r.alloc(n); dl.w0.alloc(n); dl.w1.alloc(n);
@@ -105,16 +102,16 @@ static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, dou
   const double emax = L.rho, emin = L.rho / p.eig_ratio;
   DevLevel &C = H.levels[l + 1];
   // pre-smoothing from the zero initial guess
-  cheb_jacobi(c, L.A, b, emin, emax, p.smooth_steps, 1.0, nullptr, x, L.w0.p, L.w1.p);
+  cheb_jacobi(c, L.A(), b, emin, emax, p.smooth_steps, 1.0, nullptr, x, L.w0.p, L.w1.p);
   // r = b - A x ; b_c = R r
-  spmv_axpby(c, L.A, x, -1.0, 1.0, b, L.r.p);
+  spmv_axpby(c, L.A(), x, -1.0, 1.0, b, L.r.p);
   spmv_store(c, L.R, L.r.p, C.b.p);
   vcycle_level(c, H, l + 1, C.b.p, C.x.p);
   // x += P x_c
   spmv_axpby(c, L.P, C.x.p, 1.0, 1.0, x, x);
   // post-smoothing on the correction equation: x += cheb(A, b - A x)
-  spmv_axpby(c, L.A, x, -1.0, 1.0, b, L.r.p);
-  cheb_jacobi(c, L.A, L.r.p, emin, emax, p.smooth_steps, 1.0, x, x, L.w0.p, L.w1.p);
+  spmv_axpby(c, L.A(), x, -1.0, 1.0, b, L.r.p);
+  cheb_jacobi(c, L.A(), L.r.p, emin, emax, p.smooth_steps, 1.0, x, x, L.w0.p, L.w1.p);
 }
 
 void amg_vcycle(Ctx &c, DevHierarchy &H, const double *b, double *x) {

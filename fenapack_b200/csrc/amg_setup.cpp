@@ -43,16 +43,26 @@ static double estimate_rho(const HostCsr &A, const std::vector<double> &dinv, in
   nrm = std::sqrt(nrm);
   for (int64_t i = 0; i < n; ++i) v[i] /= nrm;
   double rho = 0.0;
+  // fixed-size chunks summed in a fixed order: the estimate (and with it the whole
+  // hierarchy) is bit-reproducible whatever the number of host threads
+  const int64_t CH = 4096, nch = (n + CH - 1) / CH;
+  std::vector<double> part(nch);
   for (int s = 0; s < steps; ++s) {
-    double acc = 0.0;
-#pragma omp parallel for schedule(static) reduction(+ : acc)
-    for (int64_t i = 0; i < n; ++i) {
-      double t = 0.0;
-      for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) t += A.val[k] * v[A.col[k]];
-      t *= dinv[i];
-      w[i] = t;
-      acc += t * t;
+#pragma omp parallel for schedule(static)
+    for (int64_t cidx = 0; cidx < nch; ++cidx) {
+      double a = 0.0;
+      const int64_t e = std::min(n, (cidx + 1) * CH);
+      for (int64_t i = cidx * CH; i < e; ++i) {
+        double t = 0.0;
+        for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) t += A.val[k] * v[A.col[k]];
+        t *= dinv[i];
+        w[i] = t;
+        a += t * t;
+      }
+      part[cidx] = a;
     }
+    double acc = 0.0;
+    for (int64_t cidx = 0; cidx < nch; ++cidx) acc += part[cidx];
     rho = std::sqrt(acc);
     if (rho == 0.0) return 1.0;
     const double inv = 1.0 / rho;

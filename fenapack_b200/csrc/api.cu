@@ -39,28 +39,58 @@ Ctx::~Ctx() {
   if (stream) cudaStreamSynchronize(stream);
   if (comm) nccl().CommDestroy(comm);
   if (pinned) cudaFreeHost(pinned);
+  for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : event_pool) cudaEventDestroy(e);
   if (ev_tic) cudaEventDestroy(ev_tic);
   if (ev_toc) cudaEventDestroy(ev_toc);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
-StageTimer::StageTimer(Ctx &ctx, const char *nm) : c(ctx), name(nm) {
-  if (!c.timers_on) return;
-  cudaEventCreate(&a);
-  cudaEventCreate(&b);
+cudaEvent_t Ctx::get_event() {
+  if (!event_pool.empty()) {
+    cudaEvent_t e = event_pool.back();
+    event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  FNP_CUDA(cudaEventCreate(&e));
+  return e;
+}
+
+void Ctx::resolve_timers() {
+  if (pending.empty()) return;
+  FNP_CUDA(cudaStreamSynchronize(stream));
+  for (auto &p : pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      Timer &t = timers[p.name];
+      t.ms += ms;
+      t.calls += 1;
+    }
+    event_pool.push_back(p.a);
+    event_pool.push_back(p.b);
+  }
+  pending.clear();
+}
+
+StageTimer::StageTimer(Ctx &ctx, const char *nm, int level) : c(ctx) {
+  if (c.timers_on < level) return;
+  name = nm;
+  a = c.get_event();
+  cudaEventRecord(a, c.stream);
+}
+StageTimer::StageTimer(Ctx &ctx, const std::string &nm, int level) : c(ctx) {
+  if (c.timers_on < level) return;
+  name = nm;
+  a = c.get_event();
   cudaEventRecord(a, c.stream);
 }
 StageTimer::~StageTimer() {
   if (!a) return;
+  cudaEvent_t b = c.get_event();
   cudaEventRecord(b, c.stream);
-  cudaEventSynchronize(b);
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, a, b);
-  Timer &t = c.timers[name];
-  t.ms += ms;
-  t.calls += 1;
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
+  c.pending.push_back({name, a, b});
+  if (c.pending.size() > 200000) c.resolve_timers();
 }
 
 // ---------------------------------------------------------------------------
@@ -151,8 +181,13 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
     c.max_it = parse_int(name, v);
   } else if (name == "ksp_pc_side") {
     FNP_REQUIRE(v == "right", FNP_ERR_OPTION, "PCDKSP uses right preconditioning only (field_split.py:53)");
+  } else if (name == "fnp_spmv_kernel") {
+    if (v == "auto") c.spmv_mode = 0;
+    else if (v == "csr") c.spmv_mode = 1;
+    else if (v == "sell") c.spmv_mode = 2;
+    else throw Error(FNP_ERR_OPTION, "option fnp_spmv_kernel: auto | csr | sell (takes effect at fnp_set_pattern)");
   } else if (name == "fnp_timers") {
-    c.timers_on = parse_int(name, v) != 0;
+    c.timers_on = parse_int(name, v);
   } else {
     throw Error(FNP_ERR_OPTION, "unknown option '" + name + "'");
   }
@@ -168,12 +203,6 @@ static void op_shape(const Ctx &c, int which, int64_t &nrows, int64_t &ncols) {
     case FNP_MAT_A10: nrows = c.n_p; ncols = c.n_u_global; break;
     default: nrows = c.n_p; ncols = c.n_p_global; break;
   }
-}
-
-static int pick_lanes(double mean_row) {
-  int lanes = 2;
-  while (lanes < 32 && lanes * 2 < mean_row + 0.5) lanes *= 2;
-  return lanes;
 }
 
 static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t *colidx) {
@@ -196,7 +225,6 @@ static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t 
   std::vector<int64_t> &perm = c.perm[which];
   perm.clear();
   bool sorted = true;
-  double maxrow = 0;
   for (int64_t i = 0; i < nrows && sorted; ++i) {
     FNP_REQUIRE(h.rowptr[i + 1] >= h.rowptr[i], FNP_ERR_ARG, "rowptr not monotone");
     for (int32_t k = h.rowptr[i] + 1; k < h.rowptr[i + 1]; ++k)
@@ -211,23 +239,11 @@ static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t 
     for (int64_t k = 0; k < nnz; ++k) h.col[k] = colidx[perm[k]];
   }
   for (int64_t i = 0; i < nrows; ++i) {
-    maxrow = std::max(maxrow, (double)(h.rowptr[i + 1] - h.rowptr[i]));
     for (int32_t k = h.rowptr[i]; k < h.rowptr[i + 1]; ++k)
       FNP_REQUIRE(h.col[k] >= 0 && h.col[k] < ncols, FNP_ERR_ARG, "column index out of range");
   }
-  DevCsr &d = c.dmat[which];
-  d.nrows = (int32_t)nrows;
-  d.ncols_own = (int32_t)ncols;
-  d.nghost = 0;
-  d.nnz = nnz;
-  d.mean_row = nrows ? (double)nnz / (double)nrows : 0.0;
-  d.max_row = maxrow;
-  d.lanes = pick_lanes(d.mean_row);
-  d.rowptr.upload(h.rowptr.data(), h.rowptr.size(), c.stream);
-  d.col.upload(h.col.data(), h.col.size(), c.stream);
-  d.val.alloc((size_t)nnz);
-  d.has_dinv = false;
-  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  static const char *names[FNP_MAT_COUNT] = {"A00", "A01", "A10", "Ap", "Mp", "Kp", "P00"};
+  csr_upload_pattern(c, c.dmat[which], h, names[which]);
   c.have_pattern[which] = true;
   c.have_values[which] = false;
 }
@@ -252,8 +268,8 @@ static void set_values(Ctx &c, int which, const double *values) {
     h.val.assign(src, src + nnz);
     src = h.val.data();
   }
-  c.dmat[which].val.upload(src, (size_t)nnz, c.stream);
-  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  const bool want_dinv = which == FNP_MAT_MP || which == FNP_MAT_AP || which == FNP_MAT_A00 || which == FNP_MAT_P00;
+  csr_set_values(c, c.dmat[which], h, src, want_dinv);
   c.have_values[which] = true;
   c.dirty[which] = true;
 }
@@ -678,6 +694,7 @@ int fnp_amg_vcycle(fnp_context *ctx, int which, const double *b, double *x, int 
 int fnp_get_timer(fnp_context *ctx, const char *name, double *ms, int64_t *calls) {
   FNP_API_BEGIN
   CTX(ctx);
+  c.resolve_timers();
   auto it = c.timers.find(name ? name : "");
   if (ms) *ms = it == c.timers.end() ? 0.0 : it->second.ms;
   if (calls) *calls = it == c.timers.end() ? 0 : it->second.calls;
@@ -687,6 +704,7 @@ int fnp_get_timer(fnp_context *ctx, const char *name, double *ms, int64_t *calls
 int fnp_reset_timers(fnp_context *ctx) {
   FNP_API_BEGIN
   CTX(ctx);
+  c.resolve_timers();
   c.timers.clear();
   FNP_API_END
 }

@@ -114,8 +114,17 @@ struct DevCsr {
   int32_t nghost = 0;        // columns [ncols_own, ncols_own+nghost) address the ghost buffer
   int64_t nnz = 0;
   int lanes = 8;             // lanes per row of the vector kernel, from the row-length histogram
+  std::string tag;           // name used by the per-kernel timers ("A00", "A00/L1", "A00/P0", ...)
   DevBuf<int32_t> rowptr, col;
   DevBuf<double> val, dinv;
+  // SELL-32-sigma copy (short-row operators): slice s holds rows sl_perm[32 s .. 32 s + 31],
+  // entries stored column-major inside the slice, padded to the slice's longest row
+  bool sell = false;
+  int32_t nslices = 0;
+  int64_t sell_entries = 0;  // padded entry count
+  DevBuf<int32_t> sl_ptr, sl_col, sl_perm;
+  DevBuf<double> sl_val;
+  std::vector<int32_t> sell_pos;   // host: CSR entry k -> position in sl_val (for value refreshes)
   bool has_dinv = false;
   double mean_row = 0.0, max_row = 0.0;
   // algorithmic bytes of one y = A x  (SURVEY 8d): 12 nnz + 4 (rows+1) + 8 rows + 8 cols
@@ -139,6 +148,11 @@ struct EpiCheb {             // out = add + c0 p0 + c1 p1 + c2 dinv (b - A p1)  
   double c0, c1, c2;
 };
 
+// Upload one operator: picks the storage format from the row-length histogram
+// (SELL-32-sigma for short rows, CSR + sub-warp-per-row kernel for long rows).
+// `val` may be null (pattern only); csr_set_values refreshes the numbers later.
+void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag);
+void csr_set_values(Ctx &c, DevCsr &A, const HostCsr &pattern, const double *val, bool want_dinv);
 void spmv_store(Ctx &c, const DevCsr &A, const double *x, double *y);
 void spmv_axpby(Ctx &c, const DevCsr &A, const double *x, double a, double b, const double *z, double *y);
 void spmv_cheb(Ctx &c, const DevCsr &A, const EpiCheb &e);
@@ -154,7 +168,6 @@ void vec_copy_bc(Ctx &c, int64_t n, const double *x, double *z, const int32_t *i
 void vec_scatter_bc(Ctx &c, double *z, const int32_t *idx, const double *val, int32_t nbc);
 void vec_gather(Ctx &c, int64_t n, const int64_t *idx, const double *src, double *dst);   // dst[i] = src[idx[i]]
 void vec_scatter(Ctx &c, int64_t n, const int64_t *idx, const double *src, double *dst);  // dst[idx[i]] = src[i]
-void extract_diag_inv(Ctx &c, DevCsr &A);
 
 // deterministic reductions (two-stage, no atomics); results land in device memory.
 // Vptrs_dev: device array of pointers to the basis vectors (allocated lazily).
@@ -196,7 +209,9 @@ struct HostHierarchy {
 void amg_build_host(const HostCsr &A, const AmgParams &p, HostHierarchy &H);
 
 struct DevLevel {
-  DevCsr A, P, R;
+  DevCsr A_own, P, R;
+  DevCsr *Ap = nullptr;      // level 0 aliases the context's operator (no second device copy)
+  DevCsr &A() { return *Ap; }
   double rho = 1.0;
   DevBuf<double> x, b, r, w0, w1;
 };
@@ -210,7 +225,7 @@ struct DevHierarchy {
   bool built = false;
 };
 
-void amg_upload(Ctx &c, DevHierarchy &H);
+void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0);
 // x = Vcycle(b), zero initial guess; b and x are level-0 sized device vectors (may not alias)
 void amg_vcycle(Ctx &c, DevHierarchy &H, const double *b, double *x);
 
@@ -238,6 +253,10 @@ struct Timer {
   double ms = 0.0;
   int64_t calls = 0;
 };
+struct PendingTimer {
+  std::string name;
+  cudaEvent_t a, b;
+};
 
 struct Ctx {
   int device = 0;
@@ -262,7 +281,8 @@ struct Ctx {
   double rtol = 1e-6, atol = 1e-50;
   int max_it = 10000;
   InnerOpts opt_u, opt_ap, opt_mp;
-  bool timers_on = false;
+  int spmv_mode = 0;            // 0 auto (by row-length histogram), 1 CSR vector kernel always, 2 SELL always
+  int timers_on = 0;            // 0 off, 1 stage timers, 2 also one timer per SpMV launch
 
   // operators
   HostCsr hmat[FNP_MAT_COUNT];          // sorted host copies (pattern always; values for AMG operators)
@@ -296,6 +316,10 @@ struct Ctx {
 
   // timers
   std::map<std::string, Timer> timers;
+  std::vector<PendingTimer> pending;      // recorded, not yet resolved (no sync on the hot path)
+  std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t get_event();
+  void resolve_timers();
   cudaEvent_t ev_tic = nullptr, ev_toc = nullptr;
 
   explicit Ctx(int dev);
@@ -307,9 +331,10 @@ struct Ctx {
 // scoped stage timer (CUDA events on the context stream); no-op unless timers_on
 struct StageTimer {
   Ctx &c;
-  const char *name;
-  cudaEvent_t a = nullptr, b = nullptr;
-  StageTimer(Ctx &ctx, const char *nm);
+  std::string name;
+  cudaEvent_t a = nullptr;
+  StageTimer(Ctx &ctx, const char *nm, int level = 1);
+  StageTimer(Ctx &ctx, const std::string &nm, int level);
   ~StageTimer();
 };
 

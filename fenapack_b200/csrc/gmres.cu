@@ -105,6 +105,7 @@ void solve_fgmres(Ctx &c, const double *b, double *x, int32_t *its_out, double *
       ++napply;
       system_matvec(c, zj, w);
       // classical Gram-Schmidt
+      StageTimer tgs(c, "FENaPack: GMRES orthogonalization");
       multi_dot_ptrs(c, n, V.ptrs.p, j + 1, w, hdev);
       allreduce_sum(c, hdev, j + 1);
       multi_axpy_norm_ptrs(c, n, V.ptrs.p, j + 1, hdev, w, hdev + j + 1);

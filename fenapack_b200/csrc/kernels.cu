@@ -9,6 +9,8 @@
 //     Chebyshev three-term updates and prolongation corrections never cost a
 //     second pass over the vectors.
 //   * reductions are two-stage and atomic-free: bit-reproducible run to run.
+#include <algorithm>
+
 #include "fnp_internal.cuh"
 
 namespace fnp {
@@ -66,9 +68,187 @@ spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__rest
   if (row < nrows && lane == 0) epilogue(epi, row, s);
 }
 
+// ---------------------------------------------------------------------------
+// SELL-32-sigma kernel (the default for short-row operators): one thread per row,
+// one warp per slice of 32 rows, entries stored column-major inside the slice.
+//   * matrix loads go straight to registers, perfectly coalesced (one 128-B line of
+//     column indices + two of values per warp instruction), evict-first;
+//   * lane r gathers x for the k-th entry of row r: the 32 rows of a slice are
+//     neighbouring dofs of the FE operator, so one gather instruction touches 2-5
+//     cache lines (15-20 when a warp walks along ONE row as the CSR kernels do);
+//   * no shared memory, no shuffles, no barriers; 4 independent entries per thread
+//     in flight.
+// Why not CSR: on B200 the L1/LSU data pipe issues one 128-B wavefront per cycle per
+// SM while HBM delivers ~44 B per cycle per SM, i.e. <= ~8.7 wavefronts per 32
+// non-zeros (384 B) at HBM speed.  Sub-warp-per-row CSR spends ~20 (scattered
+// gathers), CSR staged through shared memory ~15 (LDGSTS + LDS + gathers); both were
+// measured LSU-bound at 35-45 % of HBM peak (profiles/r01_spmv_kernel_choice.md).
+// SELL needs ~3 + 3..5.  Rows are sorted by length inside windows of SIGMA rows so
+// the padding stays at a few per cent.
+// ---------------------------------------------------------------------------
+constexpr int SELL_C = 32;
+constexpr int SELL_SIGMA = 1024;
+
+template <class Epi>
+__global__ void __launch_bounds__(256)
+spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t *__restrict__ col,
+                 const double *__restrict__ val, const int32_t *__restrict__ perm, const double *__restrict__ x,
+                 Epi epi) {
+  const int slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slice >= nslices) return;
+  const int base = __ldg(sl_ptr + slice);
+  const int len = (__ldg(sl_ptr + slice + 1) - base) >> 5;
+  const int row = __ldg(perm + slice * SELL_C + lane);
+  const int32_t *cp = col + base + lane;
+  const double *vp = val + base + lane;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int k = 0;
+  for (; k + 4 <= len; k += 4) {
+    const int c0 = __ldcs(cp + (k + 0) * SELL_C), c1 = __ldcs(cp + (k + 1) * SELL_C);
+    const int c2 = __ldcs(cp + (k + 2) * SELL_C), c3 = __ldcs(cp + (k + 3) * SELL_C);
+    const double v0 = __ldcs(vp + (k + 0) * SELL_C), v1 = __ldcs(vp + (k + 1) * SELL_C);
+    const double v2 = __ldcs(vp + (k + 2) * SELL_C), v3 = __ldcs(vp + (k + 3) * SELL_C);
+    s0 += v0 * __ldg(x + c0);
+    s1 += v1 * __ldg(x + c1);
+    s2 += v2 * __ldg(x + c2);
+    s3 += v3 * __ldg(x + c3);
+  }
+  for (; k < len; ++k) s0 += __ldcs(vp + k * SELL_C) * __ldg(x + __ldcs(cp + k * SELL_C));
+  if (row >= 0) epilogue(epi, row, (s0 + s1) + (s2 + s3));
+}
+
+static int pick_lanes(double mean_row) {
+  int lanes = 2;
+  while (lanes < 32 && lanes * 2 < mean_row + 0.5) lanes *= 2;
+  return lanes;
+}
+
+// Build the SELL-32-sigma layout of a pattern: permutation, slice pointers, padded
+// column array and the CSR->SELL position map (kept on the host for value refreshes).
+static void build_sell(Ctx &c, DevCsr &A, const HostCsr &h) {
+  const int64_t n = h.nrows;
+  const int64_t nsl = (n + SELL_C - 1) / SELL_C;
+  std::vector<int32_t> perm((size_t)nsl * SELL_C, -1);
+  for (int64_t w0 = 0; w0 < n; w0 += SELL_SIGMA) {
+    const int64_t w1 = std::min<int64_t>(n, w0 + SELL_SIGMA);
+    for (int64_t i = w0; i < w1; ++i) perm[i] = (int32_t)i;
+    std::stable_sort(perm.begin() + w0, perm.begin() + w1, [&](int32_t a, int32_t b) {
+      return h.rowptr[a + 1] - h.rowptr[a] > h.rowptr[b + 1] - h.rowptr[b];
+    });
+  }
+  std::vector<int32_t> ptr(nsl + 1, 0);
+  int64_t total = 0;
+  for (int64_t s = 0; s < nsl; ++s) {
+    int32_t len = 0;
+    for (int l = 0; l < SELL_C; ++l) {
+      const int32_t r = perm[s * SELL_C + l];
+      if (r >= 0) len = std::max(len, h.rowptr[r + 1] - h.rowptr[r]);
+    }
+    total += (int64_t)len * SELL_C;
+    FNP_REQUIRE(total < (int64_t)INT32_MAX, FNP_ERR_ARG, "SELL layout exceeds 2^31 entries on one rank");
+    ptr[s + 1] = (int32_t)total;
+  }
+  std::vector<int32_t> col((size_t)total);
+  A.sell_pos.assign((size_t)h.nnz(), 0);
+#pragma omp parallel for schedule(static)
+  for (int64_t s = 0; s < nsl; ++s) {
+    const int32_t base = ptr[s];
+    const int32_t len = (ptr[s + 1] - base) / SELL_C;
+    for (int l = 0; l < SELL_C; ++l) {
+      const int32_t r = perm[s * SELL_C + l];
+      const int32_t b = r >= 0 ? h.rowptr[r] : 0, e = r >= 0 ? h.rowptr[r + 1] : 0;
+      const int32_t fill = e > b ? h.col[b] : 0;       // padding: zero value, harmless in-range column
+      for (int32_t k = 0; k < len; ++k) {
+        const int32_t dst = base + k * SELL_C + l;
+        if (b + k < e) {
+          col[dst] = h.col[b + k];
+          A.sell_pos[b + k] = dst;
+        } else {
+          col[dst] = fill;
+        }
+      }
+    }
+  }
+  A.nslices = (int32_t)nsl;
+  A.sell_entries = total;
+  A.sl_ptr.upload(ptr.data(), ptr.size(), c.stream);
+  A.sl_perm.upload(perm.data(), perm.size(), c.stream);
+  A.sl_col.upload(col.data(), col.size(), c.stream);
+  A.sl_val.alloc((size_t)total);
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  A.sell = true;
+}
+
+void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag) {
+  A.tag = tag;
+  A.nrows = (int32_t)h.nrows;
+  A.ncols_own = (int32_t)h.ncols;
+  A.nghost = 0;
+  A.nnz = h.nnz();
+  A.mean_row = h.nrows ? (double)A.nnz / (double)h.nrows : 0.0;
+  double maxrow = 0;
+  for (int64_t i = 0; i < h.nrows; ++i) maxrow = std::max(maxrow, (double)(h.rowptr[i + 1] - h.rowptr[i]));
+  A.max_row = maxrow;
+  A.lanes = pick_lanes(A.mean_row);
+  A.has_dinv = false;
+  A.sell = false;
+  A.rowptr.upload(h.rowptr.data(), h.rowptr.size(), c.stream);
+  // format choice from the row-length histogram: thread-per-row SELL needs many short
+  // rows; long rows (dense coarse levels, the divergence block) keep CSR + one
+  // sub-warp per row, which already has enough loads in flight per row
+  const bool short_rows = A.mean_row < 64.0 && maxrow <= 8.0 * std::max(8.0, A.mean_row) && h.nrows >= 4096;
+  const bool use_sell = c.spmv_mode == 2 || (c.spmv_mode == 0 && short_rows);
+  if (use_sell) {
+    build_sell(c, A, h);
+    A.col.release();
+    A.val.release();
+  } else {
+    A.col.upload(h.col.data(), h.col.size(), c.stream);
+    A.val.alloc((size_t)A.nnz);
+    A.sell_pos.clear();
+    A.sell_pos.shrink_to_fit();
+  }
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+void csr_set_values(Ctx &c, DevCsr &A, const HostCsr &h, const double *val, bool want_dinv) {
+  const int64_t nnz = h.nnz();
+  if (A.sell) {
+    std::vector<double> tmp((size_t)A.sell_entries, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < nnz; ++k) tmp[A.sell_pos[k]] = val[k];
+    A.sl_val.upload(tmp.data(), tmp.size(), c.stream);
+    FNP_CUDA(cudaStreamSynchronize(c.stream));       // tmp is pageable and goes out of scope
+  } else {
+    A.val.upload(val, (size_t)nnz, c.stream);
+  }
+  if (want_dinv) {
+    std::vector<double> dinv((size_t)h.nrows, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < h.nrows; ++i) {
+      double d = 0.0;
+      for (int32_t k = h.rowptr[i]; k < h.rowptr[i + 1]; ++k)
+        if (h.col[k] == i) d = val[k];
+      dinv[i] = d != 0.0 ? 1.0 / d : 0.0;
+    }
+    A.dinv.upload(dinv.data(), dinv.size(), c.stream);
+    A.has_dinv = true;
+  }
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+}
+
 template <class Epi>
 static void spmv_launch(Ctx &c, const DevCsr &A, const double *x, const Epi &epi) {
   if (A.nrows == 0) return;
+  StageTimer kt(c, "spmv " + A.tag, 2);
+  if (A.sell) {
+    const int threads = 256;
+    const int grid = (int)(((int64_t)A.nslices * 32 + threads - 1) / threads);
+    spmv_sell_kernel<Epi><<<grid, threads, 0, c.stream>>>(A.nslices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p, A.sl_perm.p, x, epi);
+    FNP_LAUNCH_CHECK(c);
+    return;
+  }
   const int threads = 256;
   auto grid = [&](int lanes) { return (int)(((int64_t)A.nrows * lanes + threads - 1) / threads); };
   switch (A.lanes) {
@@ -86,25 +266,6 @@ void spmv_axpby(Ctx &c, const DevCsr &A, const double *x, double a, double b, co
   spmv_launch(c, A, x, EpiAxpby{y, z, a, b});
 }
 void spmv_cheb(Ctx &c, const DevCsr &A, const EpiCheb &e) { spmv_launch(c, A, e.p1, e); }
-
-__global__ void diag_inv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                                const double *__restrict__ val, double *__restrict__ dinv) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= nrows) return;
-  double d = 0.0;
-  for (int k = rowptr[r]; k < rowptr[r + 1]; ++k)
-    if (col[k] == r) d = val[k];
-  dinv[r] = d != 0.0 ? 1.0 / d : 0.0;
-}
-
-void extract_diag_inv(Ctx &c, DevCsr &A) {
-  A.dinv.ensure(A.nrows);
-  if (A.nrows) {
-    diag_inv_kernel<<<(A.nrows + 255) / 256, 256, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, A.dinv.p);
-    FNP_LAUNCH_CHECK(c);
-  }
-  A.has_dinv = true;
-}
 
 // ---------------------------------------------------------------------------
 // BLAS-1 class

@@ -141,6 +141,7 @@ void schur_apply(Ctx &c, const double *x, double *y) {
 }
 
 void pc_apply(Ctx &c, const double *x_u, const double *x_p, double *y_u, double *y_p) {
+  FNP_REQUIRE(c.n_u_global > 0, FNP_ERR_STATE, "this context holds the Schur-complement operators only (n_u = 0)");
   StageTimer t(c, "FENaPack: PCD fieldsplit apply");
   // y_p = S^-1 x_p
   schur_apply(c, x_p, y_p);
@@ -169,26 +170,28 @@ void system_matvec(Ctx &c, const double *x, double *y) {
 static void build_amg(Ctx &c, int which, DevHierarchy &H, const AmgParams &p) {
   H.params = p;
   amg_build_host(c.hmat[which], p, H.host);
-  amg_upload(c, H);
+  amg_upload(c, H, which == FNP_MAT_AP ? "Ap" : "A00", &c.dmat[which]);
 }
 
 void setup_all(Ctx &c) {
   StageTimer t(c, "FENaPack: setup");
   FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must be called before fnp_setup");
-  const int required[] = {FNP_MAT_A00, FNP_MAT_A01, FNP_MAT_A10, FNP_MAT_AP, FNP_MAT_MP, FNP_MAT_KP};
-  for (int w : required)
+  // pressure side is always needed; the velocity side only when the context owns the
+  // whole block-triangular apply (n_u == 0: Schur-complement-only mode, the python-PC path)
+  for (int w : {(int)FNP_MAT_AP, (int)FNP_MAT_MP, (int)FNP_MAT_KP})
     FNP_REQUIRE(c.have_values[w], FNP_ERR_STATE, "fnp_setup: operator " + std::to_string(w) + " has no values");
+  const bool have_u = c.n_u_global > 0;
+  if (have_u)
+    for (int w : {(int)FNP_MAT_A00, (int)FNP_MAT_A01, (int)FNP_MAT_A10})
+      FNP_REQUIRE(c.have_values[w], FNP_ERR_STATE, "fnp_setup: operator " + std::to_string(w) + " has no values");
   FNP_REQUIRE(c.variant == 1 || c.variant == 2, FNP_ERR_STATE, "PCD variant not set");
   for (auto &b : c.p_w) b.ensure((size_t)c.n_p);
   for (auto &b : c.u_w) b.ensure((size_t)c.n_u);
   c.red_out.ensure(256);
-  // Jacobi diagonals
   const int uidx = c.velocity_pc_index();
-  for (int w : {(int)FNP_MAT_MP, (int)FNP_MAT_AP, uidx})
-    if (c.dirty[w] || !c.dmat[w].has_dinv) extract_diag_inv(c, c.dmat[w]);
   // AMG hierarchies (Ap: once; velocity block: whenever its values changed)
   if (c.opt_ap.pc == PC_AMG && (c.dirty[FNP_MAT_AP] || !c.amg_ap.built)) build_amg(c, FNP_MAT_AP, c.amg_ap, c.opt_ap.amg);
-  if (c.opt_u.pc == PC_AMG && (c.dirty[uidx] || !c.amg_u.built)) build_amg(c, uidx, c.amg_u, c.opt_u.amg);
+  if (have_u && c.opt_u.pc == PC_AMG && (c.dirty[uidx] || !c.amg_u.built)) build_amg(c, uidx, c.amg_u, c.opt_u.amg);
   for (int w = 0; w < FNP_MAT_COUNT; ++w) c.dirty[w] = false;
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   c.is_setup = true;

@@ -1,0 +1,268 @@
+"""PCD-fieldsplit-preconditioned GMRES -- drop-in for fenapack/field_split.py.
+
+``PCDKSP`` keeps the reference interface (``PCDKSP(comm)``, ``setOperators``,
+``setOptionsPrefix`` before ``init_pcd`` only, ``setFromOptions``,
+``init_pcd(pcd_assembler, pcd_pc_class=None)`` exactly once, ``solve(b, x)``)
+and the fixed configuration of the reference constructor (field_split.py:46-57:
+GMRES, right preconditioning, FIELDSPLIT / SCHUR / UPPER / USER).  In the
+reference those are PETSc objects wired together on the host; here the whole
+Krylov loop is device resident: ``solve`` makes ONE call into the C ABI
+(``fnp_solve_monolithic``), so only ``b`` and ``x`` cross PCIe per linear solve
+("PCIe").
+
+With real petsc4py a maintainer may instead keep PETSc's own KSP/PCFIELDSPLIT and
+attach ``PCDPC_BRM1/2`` as the python context of the "p" sub-PC -- the
+per-apply compatibility mode described in INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import importlib
+
+import numpy as np
+
+from . import capi
+from ._backend import PETSc
+from .field_split_backend import PCDInterface
+from .preconditioners import BasePCDPC, PCDPC_BRM1
+from .utils import allow_only_one_call
+
+_OUTER_KEYS = ("ksp_type", "ksp_gmres_restart", "ksp_rtol", "ksp_atol", "ksp_max_it")
+_U_KEYS = ("ksp_type", "ksp_max_it", "pc_type", "pc_hypre_type", "pc_amg_threshold", "pc_amg_levels",
+           "pc_amg_coarse_size", "pc_amg_smooth_steps", "pc_amg_eig_ratio")
+
+
+def dofmap_dofs_is(dofmap):
+    """Index set of the dofs owned by a sub-space (reference _field_split_utils.py:39-50)."""
+    return PETSc.IS(np.asarray(dofmap.dofs(), dtype=np.int64))
+
+
+class _SubPC(object):
+    """Stand-in for the "p" sub-PC that PETSc's fieldsplit would own."""
+
+    def __init__(self, comm, prefix):
+        self.comm = comm
+        self._prefix = prefix
+        self._ctx = None
+
+    def getOptionsPrefix(self):
+        return self._prefix
+
+    def setPythonContext(self, ctx):
+        self._ctx = ctx
+        ctx.create(self)
+
+    def getPythonContext(self):
+        return self._ctx
+
+
+class PCDKSP(object):
+    """GMRES with right fieldsplit preconditioning using upper Schur factorization
+    and PCD Schur complement approximation, solved on the GPU."""
+
+    def __init__(self, comm=None, device=0):
+        self.comm = comm if comm is not None else PETSc.COMM_WORLD
+        self._device = device
+        self._prefix = ""
+        self._A = self._P = None
+        self._ctx = None
+        self._outer_opts = {"ksp_type": "gmres"}       # PETSc.KSP.Type.GMRES, field_split.py:52
+        self._u_opts = {}
+        self._its = 0
+        self._rnorm = 0.0
+        self._reason = 0
+        self._state = None
+        self._setup_done = False
+
+    # -- configuration -----------------------------------------------------------
+    def setOptionsPrefix(self, prefix):
+        self._prefix = prefix or ""
+
+    def getOptionsPrefix(self):
+        return self._prefix
+
+    def _forbid_setOptionsPrefix(self, prefix):
+        raise RuntimeError("Options prefix cannot be set now. Set it before init_pcd.")
+
+    def setOperators(self, A, P=None):
+        self._A, self._P = A, (P if P is not None else A)
+
+    def getOperators(self):
+        return self._A, self._P
+
+    def setTolerances(self, rtol=None, atol=None, max_it=None):
+        if rtol is not None:
+            self._outer_opts["ksp_rtol"] = rtol
+        if atol is not None:
+            self._outer_opts["ksp_atol"] = atol
+        if max_it is not None:
+            self._outer_opts["ksp_max_it"] = max_it
+        if self._ctx is not None:
+            self._ctx.set_options(self._outer_opts)
+
+    def setFromOptions(self):
+        opts = PETSc.Options(self._prefix)
+        for key in _OUTER_KEYS:
+            val = opts.getString(key, None)
+            if val is not None:
+                self._outer_opts[key] = val
+        uopts = PETSc.Options(self._prefix + "fieldsplit_u_")
+        for key in _U_KEYS:
+            val = uopts.getString(key, None)
+            if val is not None:
+                if key == "pc_type" and val in ("lu", "cholesky"):
+                    raise RuntimeError("fieldsplit_u_pc_type=%s: sparse direct solves are not provided on the "
+                                       "device; use richardson + amg (demo_navier-stokes-pcd.py:153-156)" % val)
+                self._u_opts["fieldsplit_u_" + key] = val
+        if self._ctx is not None:
+            self._ctx.set_options(self._outer_opts)
+            self._ctx.set_options(self._u_opts)
+
+    # -- two-phase initialisation (reference field_split.py:61-144) ---------------
+    @allow_only_one_call
+    def init_pcd(self, pcd_assembler, pcd_pc_class=None):
+        """Initialize from a ``PCDAssembler``.  Needs to be called after
+        ``setOperators``; calls ``setFromOptions`` for all sub-solvers."""
+        if self._A is None:
+            raise RuntimeError("init_pcd: setOperators must be called first")
+        V = pcd_assembler.function_space()
+        is0 = dofmap_dofs_is(V.sub(0).dofmap())
+        is1 = dofmap_dofs_is(V.sub(1).dofmap())
+        self.is_u, self.is_p = is0, is1
+        # From now on forbid setting options prefix
+        self.setOptionsPrefix = self._forbid_setOptionsPrefix
+        self.setFromOptions()
+
+        # device context owning the whole block-triangular apply
+        ctx = capi.Context(self._device)
+        ctx.set_layout(is0.getSize(), is1.getSize())
+        ctx.set_index_sets(is0.getIndices(), is1.getIndices())
+        self._ctx = ctx
+
+        # PCD PC class: option > argument > default (field_split.py:109-124)
+        pcd_pc_prefix = self._prefix + "fieldsplit_p_"
+        sub_pc = _SubPC(self.comm, pcd_pc_prefix)
+        name = PETSc.Options(pcd_pc_prefix).getString("pc_python_type", "")
+        if name:
+            mod, _, cls = name.rpartition(".")
+            if mod == "fenapack":
+                mod = "fenapack_b200"
+            pcd_pc = getattr(importlib.import_module(mod), cls)()
+        elif pcd_pc_class is not None:
+            pcd_pc = pcd_pc_class()
+        else:
+            pcd_pc = PCDPC_BRM1()
+        if not isinstance(pcd_pc, BasePCDPC):
+            raise TypeError("PCD PC class must derive from BasePCDPC")
+        sub_pc.setPythonContext(pcd_pc)
+        pcd_pc._attach(ctx)
+        pcd_pc.setFromOptions(sub_pc)
+        ctx.set_options(self._outer_opts)
+        ctx.set_options(self._u_opts)
+        self._sub_pc, self._pcd_pc = sub_pc, pcd_pc
+
+        pcd_interface = PCDInterface(pcd_assembler, self._A, is0, is1, deep_submats=True, device=self._device)
+        try:
+            pcd_pc.init_pcd(pcd_interface)
+        except Exception:
+            print("Initialization of PCD PC from PCDAssembler failed!")
+            print("Maybe wrong PCD PC class or PCDAssembler instance.")
+            raise
+        self._setup()
+
+    # -- set-up / value refresh -------------------------------
+    def _blocks(self):
+        A, P = self._A, self._P
+        out = {capi.MAT_A00: A.createSubMatrix(self.is_u, self.is_u),
+               capi.MAT_A01: P.createSubMatrix(self.is_u, self.is_p),
+               capi.MAT_A10: A.createSubMatrix(self.is_p, self.is_u)}
+        if P is not A:
+            out[capi.MAT_P00] = P.createSubMatrix(self.is_u, self.is_u)
+        return out
+
+    def _operator_state(self):
+        return (getattr(self._A, "state", None), getattr(self._P, "state", None))
+
+    def _setup(self):
+        """PCSetUp chain: (re-)extract the blocks of the in-place re-assembled
+        operators -- pattern once, values every time -- then the python PC's setUp."""
+        ctx = self._ctx
+        first = not self._setup_done
+        for which, mat in self._blocks().items():
+            indptr, indices, data = mat.getValuesCSR()
+            if first:
+                ctx.set_pattern(which, indptr, indices)
+            if first or which in (capi.MAT_A00, capi.MAT_P00):
+                ctx.set_values(which, data)
+        self._pcd_pc.setUp(self._sub_pc)
+        ctx.setup()
+        self._state = self._operator_state()
+        self._setup_done = True
+
+    # -- solve --------------------------------------------------------------------
+    def solve(self, b, x):
+        if self._ctx is None:
+            raise RuntimeError("PCDKSP.solve: init_pcd has not been called")
+        if self._operator_state() != self._state:
+            self._setup()
+        ba = b.getArray() if hasattr(b, "getArray") else np.asarray(b)
+        sol, its, rn, nap = self._ctx.solve_monolithic(ba)
+        xa = x.getArray() if hasattr(x, "getArray") else x
+        xa[:] = sol
+        self._its, self._rnorm = its, rn
+        hist = self._ctx.residual_history()
+        rtol = float(self._outer_opts.get("ksp_rtol", 1e-5 if False else 1e-6))
+        self._reason = 2 if (len(hist) and rn <= max(rtol * hist[0], 1e-50)) else -3
+        return its
+
+    def getIterationNumber(self):
+        return self._its
+
+    def getResidualNorm(self):
+        return self._rnorm
+
+    def getConvergedReason(self):
+        return self._reason
+
+    def getConvergenceHistory(self):
+        return self._ctx.residual_history()
+
+    def device_context(self):
+        return self._ctx
+
+
+class PCDKrylovSolver(object):
+    """Counterpart of the reference's ``dolfin.PETScKrylovSolver`` subclass
+    (field_split.py:153-187)."""
+
+    def __init__(self, comm=None, device=0):
+        self._ksp = PCDKSP(comm=comm, device=device)
+        self.parameters = {"relative_tolerance": 1e-6, "absolute_tolerance": 1e-50, "maximum_iterations": 10000,
+                           "error_on_nonconvergence": True}
+
+    def init_pcd(self, pcd_assembler, pcd_pc_class=None):
+        self._ksp.init_pcd(pcd_assembler, pcd_pc_class=pcd_pc_class)
+
+    def ksp(self):
+        return self._ksp
+
+    def set_options_prefix(self, prefix):
+        self._ksp.setOptionsPrefix(prefix)
+
+    def get_options_prefix(self):
+        return self._ksp.getOptionsPrefix()
+
+    def set_from_options(self):
+        self._ksp.setFromOptions()
+
+    def set_operators(self, A, P):
+        self._ksp.setOperators(A, P)
+
+    def solve(self, x, b):
+        """dolfin.PETScKrylovSolver.solve(x, b) argument order."""
+        self._ksp.setTolerances(rtol=self.parameters["relative_tolerance"],
+                                atol=self.parameters["absolute_tolerance"],
+                                max_it=self.parameters["maximum_iterations"])
+        its = self._ksp.solve(b, x)
+        if self._ksp.getConvergedReason() < 0 and self.parameters["error_on_nonconvergence"]:
+            raise RuntimeError("PCDKrylovSolver: Krylov solver did not converge in %d iterations" % its)
+        return its

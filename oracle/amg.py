@@ -63,10 +63,17 @@ def strength_graph(A, theta):
     return S
 
 
-def aggregate_greedy(S):
+def aggregate_greedy(S, use_c=None):
     """Three-phase greedy aggregation on the strength graph S (CSR, values =
-    |a_ij|).  Returns agg[n] (aggregate id or -1) and the number of aggregates."""
+    |a_ij|).  Returns agg[n] (aggregate id or -1) and the number of aggregates.
+    For large graphs the identical loop in oracle/pcd_ref.c is used when the C
+    library is built (tests/test_oracle.py checks the two against each other)."""
     n = S.shape[0]
+    if use_c is None:
+        use_c = n > 20000
+    if use_c:
+        from . import cref
+        return cref.aggregate_greedy(S)
     ip, ix, vals = S.indptr, S.indices, S.data
     agg = np.full(n, -1, dtype=np.int64)
     nagg = 0

@@ -1,0 +1,188 @@
+"""Drop-in API tests: the reference's Python surface (PCDKSP, PCDKrylovSolver,
+PCDAssembler, PCDNewtonSolver, PCDPC_BRM1/2 as python-PC contexts) driving
+libfenapack_cuda.  Mirrors test/unit/test_fieldsplit.py (prefix handling) and the
+convergence assertion of test/bench/test_pcd_scaling.py:223."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+import fenapack_b200 as fp
+from fenapack_b200.petsc_shim import PC, Mat, Options, Vec
+from fenapack_b200.field_split_backend import PCDInterface
+from fenapack_b200.field_split import dofmap_dofs_is
+
+from fem_forms import BFSModel
+
+
+def make_assembler(model, stabilised=False):
+    return fp.PCDAssembler(model.a, model.L, [], model.a_pc if stabilised else None, ap=model.ap, kp=model.kp,
+                           mp=model.mp, bcs_pcd=model.bc_pcd, function_space=model.W)
+
+
+def set_iterative_options(prefix, variant):
+    o = Options(prefix)
+    o.setValue("ksp_gmres_restart", 150)
+    o.setValue("fieldsplit_p_pc_python_type", "fenapack.PCDPC_" + variant)
+    o.setValue("fieldsplit_u_ksp_type", "richardson")
+    o.setValue("fieldsplit_u_ksp_max_it", 1)
+    o.setValue("fieldsplit_u_pc_type", "hypre")
+    o.setValue("fieldsplit_u_pc_hypre_type", "boomeramg")
+    o.setValue("fieldsplit_p_PCD_Ap_ksp_type", "richardson")
+    o.setValue("fieldsplit_p_PCD_Ap_ksp_max_it", 2)
+    o.setValue("fieldsplit_p_PCD_Ap_pc_type", "hypre")
+    o.setValue("fieldsplit_p_PCD_Ap_pc_hypre_type", "boomeramg")
+    o.setValue("fieldsplit_p_PCD_Mp_ksp_type", "chebyshev")
+    o.setValue("fieldsplit_p_PCD_Mp_ksp_max_it", 5)
+    o.setValue("fieldsplit_p_PCD_Mp_ksp_chebyshev_eigenvalues", "0.5, 2.0")
+    o.setValue("fieldsplit_p_PCD_Mp_pc_type", "jacobi")
+
+
+def test_allow_only_one_call_and_public_names():
+    from fenapack_b200.utils import allow_only_one_call
+
+    class A:
+        @allow_only_one_call
+        def f(self):
+            return 1
+    a = A()
+    assert a.f() == 1
+    with pytest.raises(RuntimeError):
+        a.f()
+    assert A().f() == 1
+    for name in ("PCDKSP", "PCDKrylovSolver", "PCDAssembler", "PCDForm", "PCDNewtonSolver", "PCDNonlinearProblem",
+                 "PCDPC_BRM1", "PCDPC_BRM2", "PCDRPC_BRM1", "PCDRPC_BRM2"):
+        assert hasattr(fp, name)
+
+
+def test_pcd_form_flags_and_assembler_defaults():
+    m = BFSModel(level=0)
+    asm = make_assembler(m)
+    assert asm.get_pcd_form("ap").is_constant() and asm.get_pcd_form("mp").is_constant()
+    assert not asm.get_pcd_form("kp").is_constant()
+    with pytest.raises(AttributeError):
+        asm.get_pcd_form("fp")
+    with pytest.raises(AttributeError):
+        fp.PCDAssembler(m.a, m.L, [], function_space=m.W).pcd_bcs()
+    Ap = Mat()
+    asm.ap(Ap)
+    d = Ap.csr.diagonal()
+    assert np.all(d[m.bc_pcd.dofs()] == 1.0)
+    sub = Ap.csr[m.bc_pcd.dofs(), :]
+    assert sub.sum() == len(m.bc_pcd.dofs())       # identity rows (symmetric application)
+
+
+def test_interface_bc_indices_follow_subfield_position():
+    m = BFSModel(level=1, variant="BRM2")
+    asm = make_assembler(m)
+    A = Mat(m.a())
+    itf = PCDInterface(asm, A, dofmap_dofs_is(m.W.sub(0).dofmap()), dofmap_dofs_is(m.W.sub(1).dofmap()))
+    idx, vals = itf.pcd_bc_indices()
+    assert np.array_equal(m.is_p[idx], m.bc_pcd.dofs()) and np.all(vals == 0.0)
+    v = Vec(np.ones(m.is_p.size))
+    itf.apply_pcd_bcs(v)
+    assert np.all(v.array[idx] == 0.0) and v.array.sum() == m.is_p.size - idx.size
+    Kp = itf.setup_mat_Kp()
+    assert itf.setup_mat_Kp(mat=Kp) is Kp           # non-constant: refilled in place
+    Mp = itf.setup_mat_Mp()
+    assert itf.setup_mat_Mp(mat=Mp) is None         # constant: not re-assembled
+
+
+@pytest.mark.gpu
+def test_set_options_prefix_before_and_after_init():
+    """Reference test/unit/test_fieldsplit.py:84-96."""
+    Options.clear()
+    m = BFSModel(level=1)
+    set_iterative_options("foo_", "BRM1")
+    Options("foo_").setValue("fieldsplit_p_PCD_Mp_ksp_max_it", 3)
+    solver = fp.PCDKrylovSolver()
+    solver.set_options_prefix("foo_")
+    solver.set_from_options()
+    A = Mat(m.a())
+    solver.set_operators(A, A)
+    solver.init_pcd(make_assembler(m))
+    assert solver.get_options_prefix() == "foo_"
+    assert solver.ksp()._pcd_pc._device_opts["fieldsplit_p_PCD_Mp_ksp_max_it"] == "3"
+    with pytest.raises(RuntimeError):
+        solver.set_options_prefix("bar_")
+    with pytest.raises(RuntimeError):
+        solver.init_pcd(make_assembler(m))          # init_pcd only once (field_split.py:60)
+    with pytest.raises(RuntimeError):
+        solver.ksp()._pcd_pc.init_pcd(None)         # PCDPC re-initialisation (preconditioners.py:66-67)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["BRM1", "BRM2"])
+def test_newton_solver_picard_bfs(variant):
+    """Nonlinear (Picard) solve through the reference-shaped API; the only thing the
+    reference asserts is convergence (test_pcd_scaling.py:223)."""
+    Options.clear()
+    m = BFSModel(level=3, variant=variant)
+    set_iterative_options("", variant)
+    linear_solver = fp.PCDKrylovSolver()
+    linear_solver.parameters["relative_tolerance"] = 1e-6
+    linear_solver.parameters["maximum_iterations"] = 600
+    linear_solver.set_from_options()
+    # stabilised a_pc for the AMG 00-block, as the reference's "iterative" set-up does
+    problem = fp.PCDNonlinearProblem(make_assembler(m, stabilised=True))
+    solver = fp.PCDNewtonSolver(linear_solver)
+    solver.parameters["relative_tolerance"] = 1e-5
+    its, converged = solver.solve(problem, m.w)
+    assert converged and 2 <= its <= 30
+    assert solver.krylov_iterations() / its < 150
+    # the converged state solves the nonlinear problem: compare with a direct Picard loop
+    ref = BFSModel(level=3, variant=variant)
+    for _ in range(its):
+        J, b = ref._system()
+        dx = spla.spsolve(J.tocsc(), b)
+        ws = np.concatenate([ref.w.array[ref.is_u], ref.w.array[ref.is_p]]) - dx
+        ref.w.array[ref.is_u] = ws[:ref.n_u]
+        ref.w.array[ref.is_p] = ws[ref.n_u:]
+    err = np.linalg.norm(m.w.array - ref.w.array) / np.linalg.norm(ref.w.array)
+    assert err < 1e-4
+    # the value refresh happened: the device Kp differs from the first (zero-wind) one
+    assert linear_solver.ksp()._pcd_pc.mat_Kp.state >= its
+
+
+@pytest.mark.gpu
+def test_python_pc_protocol_schur_only_mode():
+    """PCDPC_BRM1 used the way PETSc's fieldsplit would use it: created through
+    setPythonContext, configured from the options database, applied to split
+    pressure vectors -- checked against the oracle."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from fenapack_b200 import capi
+    from oracle import petsc_algos as pa
+    from util import oracle_hierarchy_from_device, relerr
+    Options.clear()
+    m = BFSModel(level=2, variant="BRM1")
+    # non-trivial wind: a Stokes solve
+    J, b = m._system()
+    dx = spla.spsolve(J.tocsc(), b)
+    ws = -dx
+    m.w.array[m.is_u] = ws[:m.n_u]
+    m.w.array[m.is_p] = ws[m.n_u:]
+    set_iterative_options("", "BRM1")
+    asm = make_assembler(m)
+    A = Mat(m.a())
+    is_u, is_p = dofmap_dofs_is(m.W.sub(0).dofmap()), dofmap_dofs_is(m.W.sub(1).dofmap())
+    pc = PC(prefix="fieldsplit_p_")
+    pc.setFromOptions()                               # instantiates fenapack.PCDPC_BRM1 by dotted name
+    ctx = pc.getPythonContext()
+    assert type(ctx).__name__ == "PCDPC_BRM1"
+    ctx.init_pcd(PCDInterface(asm, A, is_u, is_p, deep_submats=True))
+    pc.setUp()
+    x = Vec(np.random.default_rng(0).standard_normal(is_p.getSize()))
+    y = x.duplicate()
+    x0 = x.array.copy()
+    pc.apply(x, y)
+    assert np.array_equal(x.array, x0)
+    Hp = oracle_hierarchy_from_device(ctx._ctx, capi.MAT_AP)
+    Mp, Ap, Kp = ctx.mat_Mp.csr, ctx.mat_Ap.csr, ctx.mat_Kp.csr
+    dinv = 1.0 / Mp.diagonal()
+    idx, vals = ctx.interface.pcd_bc_indices()
+    ref = pa.brm1_apply(x0, lambda r: pa.richardson(Ap, Hp, r, 2), Kp,
+                        lambda r: pa.chebyshev_jacobi(Mp, dinv, r, 0.5, 2.0, 5), idx, vals)
+    assert relerr(y.array, ref) <= 1e-8
+    with pytest.raises(ValueError):
+        pc.apply(x, x)

@@ -183,3 +183,56 @@ def test_error_conventions():
         ctx.set_layout(10, 4)      # re-initialisation is rejected (field_split.py:60)
     assert e.value.code == capi.ERR_STATE
     ctx.close()
+
+
+@pytest.mark.parametrize("kernel", ["csr", "sell"])
+def test_spmv_kernel_variants(kernel):
+    """Both storage formats / kernels (CSR sub-warp-per-row and SELL-32-sigma
+    thread-per-row) against the oracle: every operator, the fused Chebyshev sweep,
+    and the whole preconditioner."""
+    prob, _ = problems.channel(12, 4, 4, variant="BRM1")
+    ctx = make_context(prob, {"fnp_spmv_kernel": kernel})
+    rng = np.random.default_rng(11)
+    for which, A in ((capi.MAT_A00, prob.A00), (capi.MAT_A01, prob.A01), (capi.MAT_A10, prob.A10),
+                     (capi.MAT_AP, prob.Ap), (capi.MAT_KP, prob.Kp)):
+        x = rng.standard_normal(A.shape[1])
+        assert relerr(ctx.spmv(which, x, A.shape[0]), A @ x) <= TOL_SPMV
+    b = rng.standard_normal(prob.n_p)
+    dinv = 1.0 / prob.Mp.diagonal()
+    assert relerr(ctx.mp_solve(b), pa.chebyshev_jacobi(prob.Mp, dinv, b, *prob.cheb_bounds, 5)) <= TOL_SPMV
+    pc = oracle_preconditioner(prob, ctx)
+    xu, xp = rng.standard_normal(prob.n_u), rng.standard_normal(prob.n_p)
+    yu, yp = ctx.pc_apply(xu, xp)
+    ru, rp = pc.apply_split(xu, xp)
+    assert relerr(yp, rp) <= TOL_PC and relerr(yu, ru) <= TOL_PC
+    ctx.close()
+
+
+@pytest.mark.parametrize("kernel", ["auto", "csr", "sell"])
+def test_spmv_ragged_and_empty_rows(kernel):
+    """Edge cases of the formats: empty rows, one very long row (auto keeps CSR for
+    it), row counts that are not a multiple of the slice height, a tiny matrix."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    for n in (5000, 4097, 33, 1):
+        A = sp.random(n, n, density=min(1.0, 20.0 / n), random_state=3, format="lil")
+        if n > 200:
+            A[17, :] = 0                                 # empty row
+            A[100, :] = rng.standard_normal(n)           # dense row
+        A = (A.tocsr() + sp.identity(n)).tocsr()
+        if n > 200:
+            A[17, 17] = 0
+            A.eliminate_zeros()
+        A.sort_indices()
+        ctx = capi.Context(0)
+        ctx.set_option("fnp_spmv_kernel", kernel)
+        ctx.set_layout(0, n)
+        ctx.set_matrix(capi.MAT_KP, A)
+        x = rng.standard_normal(n)
+        assert relerr(ctx.spmv(capi.MAT_KP, x, n), A @ x) <= TOL_SPMV
+        # value-only refresh goes through the CSR -> SELL position map
+        A2 = A.copy()
+        A2.data = rng.standard_normal(A2.nnz)
+        ctx.set_values(capi.MAT_KP, A2.data)
+        assert relerr(ctx.spmv(capi.MAT_KP, x, n), A2 @ x) <= TOL_SPMV
+        ctx.close()
