@@ -34,6 +34,7 @@ OPTIONS = {
     "ksp_type": "fgmres",
     "ksp_gmres_restart": 150,
     "ksp_rtol": 1e-6,
+    "ksp_max_it": 400,
     "fieldsplit_u_ksp_type": "richardson",
     "fieldsplit_u_ksp_max_it": 1,
     "fieldsplit_u_pc_type": "hypre",

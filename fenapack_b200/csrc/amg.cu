@@ -57,9 +57,15 @@ void cheb_jacobi(Ctx &c, const DevCsr &A, const double *b, double emin, double e
   }
 }
 
-static void upload_csr(Ctx &c, const HostCsr &h, DevCsr &d, const std::string &tag) {
+static void upload_csr(Ctx &c, const HostCsr &h, DevCsr &d, const std::string &tag,
+                       std::shared_ptr<HaloPlan> halo = nullptr, int64_t n_own = -1) {
   csr_upload_pattern(c, d, h, tag);
   csr_set_values(c, d, h, h.val.data(), false);
+  if (halo) {
+    d.halo = halo;
+    d.ncols_own = (int32_t)n_own;
+    d.nghost = halo->nghost;
+  }
 }
 
 void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0) {
@@ -74,7 +80,7 @@ void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0
       FNP_REQUIRE(level0->has_dinv && level0->nrows == hl.A.nrows, FNP_ERR_STATE, "AMG level 0 operator mismatch");
     } else {
       dl.Ap = &dl.A_own;
-      upload_csr(c, hl.A, dl.A_own, name + "/L" + std::to_string(l));
+      upload_csr(c, hl.A, dl.A_own, name + "/L" + std::to_string(l), hl.halo, hl.n_own);
       dl.A_own.dinv.upload(hl.dinv.data(), hl.dinv.size(), c.stream);
       dl.A_own.has_dinv = true;
     }
@@ -87,6 +93,9 @@ void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0
     dl.x.alloc(n); dl.b.alloc(n); dl.r.alloc(n); dl.w0.alloc(n); dl.w1.alloc(n);
   }
   H.coarse_n = (int)H.host.levels.back().A.nrows;
+  H.coarse_cols = (int)H.host.coarse_cols;
+  H.coarse_maxloc = (int)H.host.coarse_maxloc;
+  if (c.nranks > 1) H.coarse_gather.alloc((size_t)(c.nranks + 1) * H.coarse_maxloc);
   H.coarse_inv.upload(H.host.coarse_inv.data(), H.host.coarse_inv.size(), c.stream);
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   H.built = true;
@@ -95,7 +104,16 @@ void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0
 static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, double *x) {
   DevLevel &L = H.levels[l];
   if (l + 1 == H.levels.size()) {
-    dense_gemv(c, H.coarse_n, H.coarse_inv.p, b, x);
+    if (c.nranks == 1) {
+      dense_gemv(c, H.coarse_n, H.coarse_cols, H.coarse_inv.p, b, x);
+    } else {
+      // padded all-gather of the coarse right-hand side, then this rank's rows of the inverse
+      double *slot = H.coarse_gather.p + (size_t)c.nranks * H.coarse_maxloc;
+      FNP_CUDA(cudaMemsetAsync(slot, 0, H.coarse_maxloc * sizeof(double), c.stream));
+      if (H.coarse_n) FNP_CUDA(cudaMemcpyAsync(slot, b, H.coarse_n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+      FNP_NCCL(nccl().AllGather(slot, H.coarse_gather.p, (size_t)H.coarse_maxloc, ncclDouble, c.comm, c.stream));
+      dense_gemv(c, H.coarse_n, H.coarse_cols, H.coarse_inv.p, H.coarse_gather.p, x);
+    }
     return;
   }
   const AmgParams &p = H.params;

@@ -31,6 +31,7 @@ static void csr_diag_inv(const HostCsr &A, std::vector<double> &dinv) {
   }
 }
 
+// power iteration on D^-1 A_dd (A_dd = diagonal block: columns owned by this rank)
 static double estimate_rho(const HostCsr &A, const std::vector<double> &dinv, int steps = 20, double safety = 1.1) {
   const int64_t n = A.nrows;
   std::vector<double> v(n), w(n);
@@ -54,7 +55,8 @@ static double estimate_rho(const HostCsr &A, const std::vector<double> &dinv, in
       const int64_t e = std::min(n, (cidx + 1) * CH);
       for (int64_t i = cidx * CH; i < e; ++i) {
         double t = 0.0;
-        for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) t += A.val[k] * v[A.col[k]];
+        for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k)
+          if (A.col[k] < n) t += A.val[k] * v[A.col[k]];
         t *= dinv[i];
         w[i] = t;
         a += t * t;
@@ -72,7 +74,8 @@ static double estimate_rho(const HostCsr &A, const std::vector<double> &dinv, in
   return safety * rho;
 }
 
-// strength graph as CSR (indices + |a_ij|)
+// strength graph of the diagonal block as CSR (indices + |a_ij|); ghost columns (>= n) are ignored,
+// so aggregates never cross rank boundaries
 static void strength(const HostCsr &A, double theta, std::vector<int32_t> &sp, std::vector<int32_t> &sc,
                      std::vector<double> &sv) {
   const int64_t n = A.nrows;
@@ -88,7 +91,7 @@ static void strength(const HostCsr &A, double theta, std::vector<int32_t> &sp, s
     for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
       const int32_t j = A.col[k];
       const double a = A.val[k];
-      if (j != i && a != 0.0 && std::fabs(a) >= theta * std::sqrt(d[i] * d[j])) ++cnt;
+      if (j != i && j < n && a != 0.0 && std::fabs(a) >= theta * std::sqrt(d[i] * d[j])) ++cnt;
     }
     sp[i + 1] = cnt;
   }
@@ -101,7 +104,7 @@ static void strength(const HostCsr &A, double theta, std::vector<int32_t> &sp, s
     for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
       const int32_t j = A.col[k];
       const double a = A.val[k];
-      if (j != i && a != 0.0 && std::fabs(a) >= theta * std::sqrt(d[i] * d[j])) {
+      if (j != i && j < n && a != 0.0 && std::fabs(a) >= theta * std::sqrt(d[i] * d[j])) {
         sc[o] = j;
         sv[o] = std::fabs(a);
         ++o;
@@ -239,7 +242,7 @@ static void transpose(const HostCsr &A, HostCsr &T) {
 
 // P = T - omega * D^-1 (A T), T given by agg / counts
 static void smoothed_prolongator(const HostCsr &A, const std::vector<double> &dinv, const std::vector<int32_t> &agg,
-                                 int64_t nagg, double omega, HostCsr &P) {
+                                 int64_t nagg, double omega, double trunc, HostCsr &P) {
   const int64_t n = A.nrows;
   std::vector<double> tval(nagg, 0.0);
   {
@@ -248,12 +251,13 @@ static void smoothed_prolongator(const HostCsr &A, const std::vector<double> &di
       if (agg[i] >= 0) cnt[agg[i]]++;
     for (int64_t a = 0; a < nagg; ++a) tval[a] = 1.0 / std::sqrt((double)cnt[a]);
   }
+  // T has one (empty) row per ghost column too: the prolongator smoothing is block local
   HostCsr T;
-  T.nrows = n;
+  T.nrows = A.ncols;
   T.ncols = nagg;
-  T.rowptr.resize(n + 1);
+  T.rowptr.resize(A.ncols + 1);
   T.rowptr[0] = 0;
-  for (int64_t i = 0; i < n; ++i) T.rowptr[i + 1] = T.rowptr[i] + (agg[i] >= 0 ? 1 : 0);
+  for (int64_t i = 0; i < A.ncols; ++i) T.rowptr[i + 1] = T.rowptr[i] + ((i < n && agg[i] >= 0) ? 1 : 0);
   T.col.resize(T.rowptr[n]);
   T.val.resize(T.rowptr[n]);
   for (int64_t i = 0; i < n; ++i)
@@ -300,6 +304,74 @@ static void smoothed_prolongator(const HostCsr &A, const std::vector<double> &di
     }
     if (!placed) { P.col[o] = a; P.val[o] = tval[a]; ++o; }
   }
+  // truncation: entries below trunc * max|row| are dropped and the row is rescaled to its
+  // former row sum (constants stay in the range of P).  Keeps the Galerkin structure while
+  // cutting the coarse stencils of P2 operators in 3D by ~4x.
+  if (trunc > 0.0) {
+    std::vector<int32_t> rp(n + 1, 0);
+    int64_t o = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      double rmax = 0.0, rs0 = 0.0, rs1 = 0.0;
+      for (int32_t k = P.rowptr[i]; k < P.rowptr[i + 1]; ++k) {
+        rmax = std::max(rmax, std::fabs(P.val[k]));
+        rs0 += P.val[k];
+      }
+      const int64_t start = o;
+      for (int32_t k = P.rowptr[i]; k < P.rowptr[i + 1]; ++k)
+        if (std::fabs(P.val[k]) >= trunc * rmax) {
+          P.col[o] = P.col[k];
+          P.val[o] = P.val[k];
+          rs1 += P.val[k];
+          ++o;
+        }
+      const double scale = rs1 != 0.0 ? rs0 / rs1 : 1.0;
+      for (int64_t k = start; k < o; ++k) P.val[k] = scale * P.val[k];
+      rp[i + 1] = (int32_t)o;
+    }
+    P.rowptr.swap(rp);
+    P.col.resize(o);
+    P.val.resize(o);
+  }
+}
+
+// Sparsify a coarse operator in place: off-diagonal entries below
+// drop*sqrt(|a_ii||a_jj|) are removed and added to the diagonal of their row.
+// `A` has local column numbering [owned | ghost]; d_ghost holds |a_jj| of the ghost
+// columns; `gcol` (optional) is the same pattern with global column ids and is
+// compacted in lock step.
+static void filter_lumped(HostCsr &A, double drop, const std::vector<double> &d_ghost, std::vector<int32_t> *gcol) {
+  if (drop <= 0.0) return;
+  const int64_t n = A.nrows;
+  std::vector<double> d(A.ncols, 0.0);
+  for (int64_t i = 0; i < n; ++i)
+    for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k)
+      if (A.col[k] == i) d[i] = std::fabs(A.val[k]);
+  for (size_t g = 0; g < d_ghost.size(); ++g) d[n + g] = d_ghost[g];
+  std::vector<int32_t> rp(n + 1, 0);
+  int64_t o = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    double lump = 0.0;
+    int64_t diag_pos = -1;
+    for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+      const int32_t j = A.col[k];
+      const double a = A.val[k];
+      if (j != i && std::fabs(a) < drop * std::sqrt(d[i] * d[j])) {
+        lump += a;
+        continue;
+      }
+      if (j == i) diag_pos = o;
+      A.col[o] = j;          // compaction in place: o <= k always
+      A.val[o] = a;
+      if (gcol) (*gcol)[o] = (*gcol)[k];
+      ++o;
+    }
+    if (diag_pos >= 0) A.val[diag_pos] += lump;
+    rp[i + 1] = (int32_t)o;
+  }
+  A.rowptr.swap(rp);
+  A.col.resize(o);
+  A.val.resize(o);
+  if (gcol) gcol->resize(o);
 }
 
 static void dense_inverse(const HostCsr &A, std::vector<double> &inv) {
@@ -335,31 +407,186 @@ static void dense_inverse(const HostCsr &A, std::vector<double> &inv) {
   }
 }
 
-void amg_build_host(const HostCsr &A0, const AmgParams &p, HostHierarchy &H) {
+// helpers from dist.cu
+std::vector<int64_t> comm_ranges(Ctx &c, int64_t n_local);
+double comm_allreduce(Ctx &c, double v, bool max_op);
+std::vector<double> comm_allgather_padded(Ctx &c, const double *v, int64_t count, int64_t maxcount);
+std::shared_ptr<HaloPlan> build_halo(Ctx &c, HostCsr &h, const std::vector<int64_t> &begins,
+                                     std::vector<int64_t> *ghost_global_out);
+std::vector<double> halo_exchange_host(Ctx &c, HaloPlan &plan, const std::vector<double> &x_own);
+
+// Rows of P for the ghost dofs of A (their owners computed them): returns P extended to
+// n_own + n_ghost rows with GLOBAL coarse column ids.
+static void extend_prolongator(Ctx &c, const HostCsr &P, int64_t coarse_begin, HaloPlan *plan, int64_t nghost,
+                               HostCsr &Pext) {
+  const int64_t n = P.nrows;
+  Pext.nrows = n + nghost;
+  Pext.ncols = 0;   // global ids; set by the caller
+  Pext.rowptr.assign(n + nghost + 1, 0);
+  for (int64_t i = 0; i < n; ++i) Pext.rowptr[i + 1] = P.rowptr[i + 1];
+  int64_t W = 0;
+  for (int64_t i = 0; i < n; ++i) W = std::max<int64_t>(W, P.rowptr[i + 1] - P.rowptr[i]);
+  W = (int64_t)comm_allreduce(c, (double)W, true);
+  std::vector<std::vector<double>> gc, gv;
+  std::vector<double> glen;
+  if (plan && nghost > 0) {
+    std::vector<double> tmp(n);
+    for (int64_t i = 0; i < n; ++i) tmp[i] = (double)(P.rowptr[i + 1] - P.rowptr[i]);
+    glen = halo_exchange_host(c, *plan, tmp);
+  } else if (plan) {
+    std::vector<double> tmp(n, 0.0);
+    halo_exchange_host(c, *plan, tmp);      // collective: every rank takes part
+  }
+  for (int64_t k = 0; k < W; ++k) {
+    std::vector<double> cc(n, -1.0), vv(n, 0.0);
+    for (int64_t i = 0; i < n; ++i)
+      if (P.rowptr[i] + k < P.rowptr[i + 1]) {
+        cc[i] = (double)(coarse_begin + P.col[P.rowptr[i] + k]);
+        vv[i] = P.val[P.rowptr[i] + k];
+      }
+    if (plan) {
+      gc.push_back(halo_exchange_host(c, *plan, cc));
+      gv.push_back(halo_exchange_host(c, *plan, vv));
+    }
+  }
+  for (int64_t g = 0; g < nghost; ++g) Pext.rowptr[n + g + 1] = Pext.rowptr[n + g] + (int32_t)glen[g];
+  Pext.col.resize(Pext.rowptr[n + nghost]);
+  Pext.val.resize(Pext.rowptr[n + nghost]);
+  for (int64_t i = 0; i < n; ++i)
+    for (int32_t k = P.rowptr[i]; k < P.rowptr[i + 1]; ++k) {
+      Pext.col[k] = (int32_t)(coarse_begin + P.col[k]);
+      Pext.val[k] = P.val[k];
+    }
+  for (int64_t g = 0; g < nghost; ++g)
+    for (int32_t k = 0; k < (int32_t)glen[g]; ++k) {
+      Pext.col[Pext.rowptr[n + g] + k] = (int32_t)gc[k][g];
+      Pext.val[Pext.rowptr[n + g] + k] = gv[k][g];
+    }
+}
+
+// Set-up of the hierarchy of one operator.  `A0` holds this rank's rows with GLOBAL
+// column ids; `begins` are the ownership offsets of all ranks.  Aggregation and
+// prolongator smoothing are local to the rank (aggregates never cross a rank
+// boundary, P and R are block diagonal over ranks); the Galerkin product couples
+// neighbouring ranks through the ghost rows of P.  With one rank this is the plain
+// serial algorithm.
+void amg_build_host(Ctx &c, const HostCsr &A0, std::vector<int64_t> begins, const AmgParams &p, HostHierarchy &H) {
   H.levels.clear();
   H.coarse_inv.clear();
-  H.levels.emplace_back();
-  H.levels.back().A = A0;
+  const int me = c.rank, R = c.nranks;
+  HostCsr Ag = A0;                 // current level, global column ids
   while (true) {
+    H.levels.emplace_back();
     HostLevel &lvl = H.levels.back();
+    lvl.A = Ag;
+    std::vector<int64_t> ghosts;
+    lvl.halo = build_halo(c, lvl.A, begins, &ghosts);     // relabels lvl.A to [owned | ghost]
+    lvl.n_own = begins[me + 1] - begins[me];
+    lvl.begins = begins;
     const HostCsr &A = lvl.A;
     csr_diag_inv(A, lvl.dinv);
-    lvl.rho = estimate_rho(A, lvl.dinv);
-    if (A.nrows <= p.coarse_size || (int)H.levels.size() >= p.max_levels) break;
+    lvl.rho = comm_allreduce(c, estimate_rho(A, lvl.dinv), true);
+    const int64_t n_global = begins[R];
+    if (n_global <= p.coarse_size || (int)H.levels.size() >= p.max_levels) break;
     std::vector<int32_t> sp, sc, agg;
     std::vector<double> sv;
     strength(A, p.theta * std::pow(0.5, (double)(H.levels.size() - 1)), sp, sc, sv);
     const int64_t nagg = aggregate_greedy(A.nrows, sp, sc, sv, agg);
-    if (nagg == 0 || nagg >= A.nrows) break;
-    smoothed_prolongator(A, lvl.dinv, agg, nagg, p.omega_scale / lvl.rho, lvl.P);
+    std::vector<int64_t> cbegins = comm_ranges(c, nagg);
+    if (cbegins[R] == 0 || cbegins[R] >= n_global) break;
+    smoothed_prolongator(A, lvl.dinv, agg, nagg, p.omega_scale / lvl.rho, p.p_trunc, lvl.P);
     transpose(lvl.P, lvl.R);
+    // Galerkin product with the ghost rows of P fetched from their owners
+    HostCsr Pext;
+    extend_prolongator(c, lvl.P, cbegins[me], lvl.halo.get(), (int64_t)ghosts.size(), Pext);
+    // compact numbering of the coarse columns that occur: [my aggregates | foreign ones, sorted]
+    std::vector<int64_t> foreign;
+    for (int64_t k = 0; k < Pext.nnz(); ++k) {
+      const int64_t g = Pext.col[k];
+      if (g < cbegins[me] || g >= cbegins[me + 1]) foreign.push_back(g);
+    }
+    std::sort(foreign.begin(), foreign.end());
+    foreign.erase(std::unique(foreign.begin(), foreign.end()), foreign.end());
+    for (int64_t k = 0; k < Pext.nnz(); ++k) {
+      const int64_t g = Pext.col[k];
+      if (g >= cbegins[me] && g < cbegins[me + 1]) Pext.col[k] = (int32_t)(g - cbegins[me]);
+      else Pext.col[k] = (int32_t)(nagg + (std::lower_bound(foreign.begin(), foreign.end(), g) - foreign.begin()));
+    }
+    Pext.ncols = nagg + (int64_t)foreign.size();
     HostCsr AP, Ac;
-    spgemm(A, lvl.P, AP);
+    spgemm(A, Pext, AP);
     spgemm(lvl.R, AP, Ac);
-    H.levels.emplace_back();
-    H.levels.back().A = std::move(Ac);
+    // back to global coarse ids, rows sorted by global column
+    std::vector<int32_t> gcol(Ac.col.size());
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < Ac.nrows; ++i) {
+      std::vector<std::pair<int32_t, double>> row;
+      for (int32_t k = Ac.rowptr[i]; k < Ac.rowptr[i + 1]; ++k) {
+        const int32_t l = Ac.col[k];
+        const int64_t g = l < nagg ? cbegins[me] + l : foreign[l - nagg];
+        row.push_back({(int32_t)g, Ac.val[k]});
+      }
+      std::sort(row.begin(), row.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+      for (int32_t k = Ac.rowptr[i]; k < Ac.rowptr[i + 1]; ++k) {
+        gcol[k] = row[k - Ac.rowptr[i]].first;
+        Ac.val[k] = row[k - Ac.rowptr[i]].second;
+      }
+    }
+    // sparsify: needs |a_jj| of the ghost columns
+    HostCsr Aloc = Ac;
+    Aloc.col = gcol;
+    Aloc.ncols = cbegins[R];
+    std::vector<int64_t> cghosts;
+    std::shared_ptr<HaloPlan> cplan = build_halo(c, Aloc, cbegins, &cghosts);
+    std::vector<double> dg;
+    if (cplan) {
+      std::vector<double> down(Aloc.nrows, 0.0);
+      for (int64_t i = 0; i < Aloc.nrows; ++i)
+        for (int32_t k = Aloc.rowptr[i]; k < Aloc.rowptr[i + 1]; ++k)
+          if (Aloc.col[k] == i) down[i] = std::fabs(Aloc.val[k]);
+      dg = halo_exchange_host(c, *cplan, down);
+    }
+    filter_lumped(Aloc, p.coarse_drop, dg, &gcol);
+    Ag = std::move(Aloc);
+    Ag.col = std::move(gcol);
+    Ag.ncols = cbegins[R];
+    begins = cbegins;
   }
-  dense_inverse(H.levels.back().A, H.coarse_inv);
+  // coarsest level: every rank inverts the (small) global matrix and keeps its own rows,
+  // columns laid out as the padded all-gather of the right-hand side delivers them
+  {
+    HostLevel &lvl = H.levels.back();
+    const int64_t n = lvl.n_own, ng = begins[R];
+    int64_t maxloc = 0;
+    for (int q = 0; q < R; ++q) maxloc = std::max(maxloc, begins[q + 1] - begins[q]);
+    FNP_REQUIRE(ng <= 8192, FNP_ERR_NUMERIC, "AMG coarsening stalled: coarsest level has " + std::to_string(ng) + " rows");
+    std::vector<double> rows((size_t)n * ng, 0.0);
+    for (int64_t i = 0; i < n; ++i)
+      for (int32_t k = Ag.rowptr[i]; k < Ag.rowptr[i + 1]; ++k) rows[(size_t)i * ng + Ag.col[k]] = Ag.val[k];
+    std::vector<double> all = comm_allgather_padded(c, rows.data(), n * ng, maxloc * ng);
+    HostCsr dense;      // reuse dense_inverse through a CSR view of the dense matrix
+    dense.nrows = dense.ncols = ng;
+    dense.rowptr.resize(ng + 1);
+    dense.col.resize((size_t)ng * ng);
+    dense.val.resize((size_t)ng * ng);
+    for (int64_t gi = 0; gi <= ng; ++gi) dense.rowptr[gi] = (int32_t)(gi * ng);
+    for (int q = 0; q < R; ++q)
+      for (int64_t i = 0; i < begins[q + 1] - begins[q]; ++i)
+        for (int64_t j = 0; j < ng; ++j) {
+          const int64_t gi = begins[q] + i;
+          dense.col[(size_t)gi * ng + j] = (int32_t)j;
+          dense.val[(size_t)gi * ng + j] = all[(size_t)q * maxloc * ng + (size_t)i * ng + j];
+        }
+    std::vector<double> inv;
+    dense_inverse(dense, inv);
+    H.coarse_cols = R * maxloc;
+    H.coarse_maxloc = maxloc;
+    H.coarse_inv.assign((size_t)n * H.coarse_cols, 0.0);
+    for (int64_t i = 0; i < n; ++i)
+      for (int q = 0; q < R; ++q)
+        for (int64_t t = 0; t < begins[q + 1] - begins[q]; ++t)
+          H.coarse_inv[(size_t)i * H.coarse_cols + q * maxloc + t] = inv[(size_t)(begins[me] + i) * ng + begins[q] + t];
+  }
 }
 
 }  // namespace fnp

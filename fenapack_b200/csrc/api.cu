@@ -9,6 +9,10 @@
 
 namespace fnp {
 
+std::vector<int64_t> comm_ranges(Ctx &c, int64_t n_local);
+std::shared_ptr<HaloPlan> build_halo(Ctx &c, HostCsr &h, const std::vector<int64_t> &begins,
+                                     std::vector<int64_t> *ghost_global_out);
+
 static thread_local std::string g_last_error;
 void set_last_error(const std::string &m) { g_last_error = m; }
 
@@ -151,6 +155,10 @@ static void set_inner_option(InnerOpts &o, const std::string &full, const std::s
   } else if (key == "pc_amg_smooth_steps") {
     o.amg.smooth_steps = parse_int(full, v);
     FNP_REQUIRE(o.amg.smooth_steps >= 1, FNP_ERR_OPTION, "option " + full + ": must be >= 1");
+  } else if (key == "pc_amg_prolongator_truncation") {
+    o.amg.p_trunc = parse_real(full, v);
+  } else if (key == "pc_amg_coarse_drop") {
+    o.amg.coarse_drop = parse_real(full, v);
   } else if (key == "pc_amg_eig_ratio") {
     o.amg.eig_ratio = parse_real(full, v);
   } else {
@@ -209,7 +217,6 @@ static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t 
   FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must precede fnp_set_pattern");
   FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT, FNP_ERR_ARG, "bad operator id");
   FNP_REQUIRE(rowptr && (colidx || rowptr[0] == 0), FNP_ERR_ARG, "null pattern");
-  FNP_REQUIRE(c.nranks == 1, FNP_ERR_STATE, "distributed patterns are handled by fnp_set_pattern in dist.cu");
   int64_t nrows, ncols;
   op_shape(c, which, nrows, ncols);
   HostCsr &h = c.hmat[which];
@@ -243,7 +250,22 @@ static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t 
       FNP_REQUIRE(h.col[k] >= 0 && h.col[k] < ncols, FNP_ERR_ARG, "column index out of range");
   }
   static const char *names[FNP_MAT_COUNT] = {"A00", "A01", "A10", "Ap", "Mp", "Kp", "P00"};
-  csr_upload_pattern(c, c.dmat[which], h, names[which]);
+  DevCsr &d = c.dmat[which];
+  if (c.nranks == 1) {
+    csr_upload_pattern(c, d, h, names[which]);
+  } else {
+    // multi-rank: the device copy uses local column numbering [owned | ghost]; the host
+    // copy keeps the global ids (the AMG set-up starts from them)
+    const bool u_cols = which == FNP_MAT_A00 || which == FNP_MAT_P00 || which == FNP_MAT_A10;
+    const std::vector<int64_t> &begins = u_cols ? c.u_begins : c.p_begins;
+    HostCsr loc = h;
+    std::shared_ptr<HaloPlan> plan = build_halo(c, loc, begins, nullptr);
+    csr_upload_pattern(c, d, loc, names[which]);
+    d.halo = plan;
+    d.ncols_own = (int32_t)(begins[c.rank + 1] - begins[c.rank]);
+    d.nghost = plan ? plan->nghost : 0;
+    c.local_cols[which] = std::move(loc.col);
+  }
   c.have_pattern[which] = true;
   c.have_values[which] = false;
 }
@@ -269,7 +291,16 @@ static void set_values(Ctx &c, int which, const double *values) {
     src = h.val.data();
   }
   const bool want_dinv = which == FNP_MAT_MP || which == FNP_MAT_AP || which == FNP_MAT_A00 || which == FNP_MAT_P00;
-  csr_set_values(c, c.dmat[which], h, src, want_dinv);
+  if (c.nranks == 1) {
+    csr_set_values(c, c.dmat[which], h, src, want_dinv);
+  } else {
+    HostCsr view;                       // same rows, local column numbering (diagonal = row index)
+    view.nrows = h.nrows;
+    view.ncols = h.ncols;
+    view.rowptr = h.rowptr;
+    view.col = c.local_cols[which];
+    csr_set_values(c, c.dmat[which], view, src, want_dinv);
+  }
   c.have_values[which] = true;
   c.dirty[which] = true;
 }
@@ -417,6 +448,11 @@ int fnp_set_layout(fnp_context *ctx, int64_t n_u_local, int64_t u_begin, int64_t
                 "single-rank context must own everything");
   c.n_u = n_u_local; c.u_begin = u_begin; c.n_u_global = n_u_global;
   c.n_p = n_p_local; c.p_begin = p_begin; c.n_p_global = n_p_global;
+  c.u_begins = comm_ranges(c, n_u_local);
+  c.p_begins = comm_ranges(c, n_p_local);
+  FNP_REQUIRE(c.u_begins[c.rank] == u_begin && c.u_begins[c.nranks] == n_u_global &&
+                  c.p_begins[c.rank] == p_begin && c.p_begins[c.nranks] == n_p_global,
+              FNP_ERR_ARG, "ownership ranges of the ranks are not contiguous / do not add up to the global sizes");
   c.have_layout = true;
   FNP_API_END
 }

@@ -1,0 +1,182 @@
+// Multi-rank plumbing: one process (or host thread) per GPU, rows of every operator
+// partitioned in contiguous ownership ranges (PETSc's MPIAIJ layout, which the
+// reference inherits from DOLFIN: fenapack/SubfieldBC.h:138-140).  The only data-path
+// exchanges are (i) the ghost entries of x before an SpMV (the MatMult VecScatter
+// of the reference) and (ii) small all-reduces for the Krylov scalars -- both NCCL
+// over NVLink, ordered on the context's stream.
+#include <algorithm>
+#include <numeric>
+
+#include "fnp_internal.cuh"
+
+namespace fnp {
+
+__global__ void pack_kernel(int32_t n, const int32_t *__restrict__ idx, const double *__restrict__ x,
+                            double *__restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = x[idx[i]];
+}
+
+void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own) {
+  StageTimer t(c, "halo exchange", 2);
+  if (h.nsend > 0) {
+    pack_kernel<<<(h.nsend + 255) / 256, 256, 0, c.stream>>>(h.nsend, h.send_idx.p, x_own, h.send_buf.p);
+    c.launches++;
+    FNP_CUDA(cudaPeekAtLastError());
+  }
+  const NcclApi &n = nccl();
+  FNP_NCCL(n.GroupStart());
+  for (int q = 0; q < c.nranks; ++q) {
+    if (h.send_count[q] > 0)
+      FNP_NCCL(n.Send(h.send_buf.p + h.send_off[q], (size_t)h.send_count[q], ncclDouble, q, c.comm, c.stream));
+    if (h.recv_count[q] > 0)
+      FNP_NCCL(n.Recv(h.ghost.p + h.recv_off[q], (size_t)h.recv_count[q], ncclDouble, q, c.comm, c.stream));
+  }
+  FNP_NCCL(n.GroupEnd());
+}
+
+// ---- small host-level collectives (set-up time), staged through device memory ----
+std::vector<int64_t> comm_allgather_i64(Ctx &c, int64_t v) {
+  std::vector<int64_t> out((size_t)c.nranks, v);
+  if (c.nranks == 1) return out;
+  DevBuf<int64_t> d((size_t)c.nranks + 1);
+  FNP_CUDA(cudaMemcpyAsync(d.p + c.nranks, &v, sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+  FNP_NCCL(nccl().AllGather(d.p + c.nranks, d.p, 1, ncclInt64, c.comm, c.stream));
+  FNP_CUDA(cudaMemcpyAsync(out.data(), d.p, c.nranks * sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  return out;
+}
+
+double comm_allreduce(Ctx &c, double v, bool max_op) {
+  if (c.nranks == 1) return v;
+  DevBuf<double> d(1);
+  FNP_CUDA(cudaMemcpyAsync(d.p, &v, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  FNP_NCCL(nccl().AllReduce(d.p, d.p, 1, ncclDouble, max_op ? ncclMax : ncclSum, c.comm, c.stream));
+  FNP_CUDA(cudaMemcpyAsync(&v, d.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  return v;
+}
+
+// Padded all-gather of host doubles: every rank contributes `count` (<= maxcount) values;
+// result is [nranks x maxcount] row-major.
+std::vector<double> comm_allgather_padded(Ctx &c, const double *v, int64_t count, int64_t maxcount) {
+  std::vector<double> out((size_t)c.nranks * maxcount, 0.0);
+  if (c.nranks == 1) {
+    std::copy(v, v + count, out.begin());
+    return out;
+  }
+  DevBuf<double> d((size_t)(c.nranks + 1) * maxcount);
+  d.zero(c.stream);
+  if (count) FNP_CUDA(cudaMemcpyAsync(d.p + (size_t)c.nranks * maxcount, v, count * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  FNP_NCCL(nccl().AllGather(d.p + (size_t)c.nranks * maxcount, d.p, (size_t)maxcount, ncclDouble, c.comm, c.stream));
+  FNP_CUDA(cudaMemcpyAsync(out.data(), d.p, out.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  return out;
+}
+
+// Ownership offsets of all ranks from the local begin: begins[q] .. begins[q+1]
+std::vector<int64_t> comm_ranges(Ctx &c, int64_t n_local) {
+  std::vector<int64_t> counts = comm_allgather_i64(c, n_local);
+  std::vector<int64_t> begins((size_t)c.nranks + 1, 0);
+  for (int q = 0; q < c.nranks; ++q) begins[q + 1] = begins[q] + counts[q];
+  return begins;
+}
+
+// Build the halo plan of a matrix whose columns are GLOBAL ids of a space partitioned
+// by `begins`, and relabel the columns in place to [owned 0..n_own) | ghosts n_own..).
+// Returns null (and only shifts the columns) on single-rank contexts.
+std::shared_ptr<HaloPlan> build_halo(Ctx &c, HostCsr &h, const std::vector<int64_t> &begins,
+                                     std::vector<int64_t> *ghost_global_out) {
+  const int R = c.nranks, me = c.rank;
+  const int64_t b0 = begins[me], b1 = begins[me + 1];
+  const int64_t n_own = b1 - b0;
+  const int64_t nnz = h.nnz();
+  if (R == 1) {
+    h.ncols = n_own;
+    if (ghost_global_out) ghost_global_out->clear();
+    return nullptr;
+  }
+  // ghost columns, sorted unique
+  std::vector<int64_t> ghosts;
+  for (int64_t k = 0; k < nnz; ++k) {
+    const int64_t g = h.col[k];
+    if (g < b0 || g >= b1) ghosts.push_back(g);
+  }
+  std::sort(ghosts.begin(), ghosts.end());
+  ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
+  const int64_t ng = (int64_t)ghosts.size();
+  FNP_REQUIRE(n_own + ng < (int64_t)INT32_MAX, FNP_ERR_ARG, "local column space exceeds 32-bit indices");
+  // relabel
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < nnz; ++k) {
+    const int64_t g = h.col[k];
+    if (g >= b0 && g < b1) {
+      h.col[k] = (int32_t)(g - b0);
+    } else {
+      const int64_t pos = std::lower_bound(ghosts.begin(), ghosts.end(), g) - ghosts.begin();
+      h.col[k] = (int32_t)(n_own + pos);
+    }
+  }
+  h.ncols = n_own + ng;
+
+  auto plan = std::make_shared<HaloPlan>();
+  plan->send_count.assign(R, 0); plan->send_off.assign(R, 0);
+  plan->recv_count.assign(R, 0); plan->recv_off.assign(R, 0);
+  // what I need from each owner (ghosts are sorted, hence grouped by owner)
+  std::vector<int32_t> request((size_t)ng);
+  {
+    int q = 0;
+    for (int64_t i = 0; i < ng; ++i) {
+      while (ghosts[i] >= begins[q + 1]) ++q;
+      plan->recv_count[q]++;
+      request[i] = (int32_t)(ghosts[i] - begins[q]);     // local index at the owner
+    }
+    for (int q2 = 1; q2 < R; ++q2) plan->recv_off[q2] = plan->recv_off[q2 - 1] + plan->recv_count[q2 - 1];
+  }
+  plan->nghost = (int32_t)ng;
+  // counts matrix: all_need[r * R + q] = what rank r needs from rank q
+  DevBuf<int32_t> d_counts((size_t)R * R + R);
+  FNP_CUDA(cudaMemcpyAsync(d_counts.p + (size_t)R * R, plan->recv_count.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+  FNP_NCCL(nccl().AllGather(d_counts.p + (size_t)R * R, d_counts.p, (size_t)R, ncclInt32, c.comm, c.stream));
+  std::vector<int32_t> all_need((size_t)R * R);
+  FNP_CUDA(cudaMemcpyAsync(all_need.data(), d_counts.p, all_need.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  int64_t nsend = 0;
+  for (int q = 0; q < R; ++q) {
+    plan->send_count[q] = all_need[(size_t)q * R + me];
+    plan->send_off[q] = (int)nsend;
+    nsend += plan->send_count[q];
+  }
+  plan->nsend = (int32_t)nsend;
+  // index lists: my requests go to the owners, their requests come to me
+  DevBuf<int32_t> d_req((size_t)std::max<int64_t>(ng, 1));
+  plan->send_idx.alloc((size_t)std::max<int64_t>(nsend, 1));
+  if (ng) FNP_CUDA(cudaMemcpyAsync(d_req.p, request.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+  const NcclApi &n = nccl();
+  FNP_NCCL(n.GroupStart());
+  for (int q = 0; q < R; ++q) {
+    if (plan->recv_count[q] > 0)
+      FNP_NCCL(n.Send(d_req.p + plan->recv_off[q], (size_t)plan->recv_count[q], ncclInt32, q, c.comm, c.stream));
+    if (plan->send_count[q] > 0)
+      FNP_NCCL(n.Recv(plan->send_idx.p + plan->send_off[q], (size_t)plan->send_count[q], ncclInt32, q, c.comm, c.stream));
+  }
+  FNP_NCCL(n.GroupEnd());
+  plan->send_buf.alloc((size_t)std::max<int64_t>(nsend, 1));
+  plan->ghost.alloc((size_t)std::max<int64_t>(ng, 1));
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  if (ghost_global_out) *ghost_global_out = ghosts;
+  return plan;
+}
+
+// Exchange one host vector through a halo plan: returns the ghost values (set-up helper).
+std::vector<double> halo_exchange_host(Ctx &c, HaloPlan &plan, const std::vector<double> &x_own) {
+  DevBuf<double> d(std::max<size_t>(x_own.size(), 1));
+  if (!x_own.empty()) FNP_CUDA(cudaMemcpyAsync(d.p, x_own.data(), x_own.size() * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  halo_exchange(c, plan, d.p);
+  std::vector<double> g((size_t)plan.nghost);
+  if (plan.nghost) FNP_CUDA(cudaMemcpyAsync(g.data(), plan.ghost.p, g.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  return g;
+}
+
+}  // namespace fnp

@@ -107,6 +107,18 @@ struct HostCsr {
 
 struct Ctx;
 
+// Halo plan of one distributed operator (multi-rank contexts): which owned entries of
+// x each peer needs (send_idx, grouped by peer) and where the entries received from
+// each peer land in the ghost buffer (ghost columns are sorted by global id, hence
+// grouped by owner).
+struct HaloPlan {
+  std::vector<int> send_count, send_off, recv_count, recv_off;   // per peer rank
+  int32_t nsend = 0, nghost = 0;
+  DevBuf<int32_t> send_idx;
+  DevBuf<double> send_buf, ghost;
+};
+void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own);
+
 // Device-resident CSR operator; columns index [x_own | x_ghost].
 struct DevCsr {
   int32_t nrows = 0;
@@ -114,6 +126,7 @@ struct DevCsr {
   int32_t nghost = 0;        // columns [ncols_own, ncols_own+nghost) address the ghost buffer
   int64_t nnz = 0;
   int lanes = 8;             // lanes per row of the vector kernel, from the row-length histogram
+  std::shared_ptr<HaloPlan> halo;   // null on single-rank contexts
   std::string tag;           // name used by the per-kernel timers ("A00", "A00/L1", "A00/P0", ...)
   DevBuf<int32_t> rowptr, col;
   DevBuf<double> val, dinv;
@@ -181,7 +194,7 @@ void multi_axpy_ptrs(Ctx &c, int64_t n, const double *const *Zptrs_dev, int nvec
 // v = w / sqrt(nrm2_dev[0])
 void vec_scale_inv_sqrt(Ctx &c, int64_t n, const double *nrm2_dev, const double *w, double *v);
 void dot(Ctx &c, int64_t n, const double *x, const double *y, double *out_dev);
-void dense_gemv(Ctx &c, int n, const double *Minv, const double *b, double *x);
+void dense_gemv(Ctx &c, int nrows, int ncols, const double *Minv, const double *b, double *x);
 
 // ---------------------------------------------------------------------------
 // AMG
@@ -193,20 +206,27 @@ struct AmgParams {
   int smooth_steps = 2;
   double eig_ratio = 10.0;
   double omega_scale = 4.0 / 3.0;
+  double p_trunc = 0.2;        // drop prolongator entries below p_trunc*max|row|, rescale to the row sum
+  double coarse_drop = 0.0;    // > 0: lump coarse entries below drop*sqrt(|a_ii||a_jj|) onto the diagonal
 };
 
 struct HostLevel {
-  HostCsr A, P, R;
+  HostCsr A, P, R;                  // A: local rows, columns [owned | ghost]; P, R: rank local
   std::vector<double> dinv;
   double rho = 1.0;
+  std::shared_ptr<HaloPlan> halo;   // null on single-rank contexts
+  int64_t n_own = 0;
+  std::vector<int64_t> begins;      // ownership offsets of this level
 };
 
 struct HostHierarchy {
   std::vector<HostLevel> levels;
-  std::vector<double> coarse_inv;   // dense row-major
+  std::vector<double> coarse_inv;   // dense row-major [n_own x coarse_cols]
+  int64_t coarse_cols = 0, coarse_maxloc = 0;
 };
 
-void amg_build_host(const HostCsr &A, const AmgParams &p, HostHierarchy &H);
+void amg_build_host(Ctx &c, const HostCsr &A_global_cols, std::vector<int64_t> begins, const AmgParams &p,
+                    HostHierarchy &H);
 
 struct DevLevel {
   DevCsr A_own, P, R;
@@ -218,8 +238,8 @@ struct DevLevel {
 
 struct DevHierarchy {
   std::vector<DevLevel> levels;
-  DevBuf<double> coarse_inv;
-  int coarse_n = 0;
+  DevBuf<double> coarse_inv, coarse_gather;
+  int coarse_n = 0, coarse_cols = 0, coarse_maxloc = 0;
   AmgParams params;
   HostHierarchy host;     // kept for introspection / refresh
   bool built = false;
@@ -269,6 +289,8 @@ struct Ctx {
   int rank = 0, nranks = 1;
   ncclComm_t comm = nullptr;
 
+  std::vector<int64_t> u_begins, p_begins;   // ownership offsets of all ranks
+
   // layout
   bool have_layout = false;
   int64_t n_u = 0, u_begin = 0, n_u_global = 0;
@@ -287,6 +309,7 @@ struct Ctx {
   // operators
   HostCsr hmat[FNP_MAT_COUNT];          // sorted host copies (pattern always; values for AMG operators)
   std::vector<int64_t> perm[FNP_MAT_COUNT];   // user order -> sorted order (empty = identity)
+  std::vector<int32_t> local_cols[FNP_MAT_COUNT];   // multi-rank: columns in local [owned | ghost] numbering
   bool have_pattern[FNP_MAT_COUNT] = {};
   bool have_values[FNP_MAT_COUNT] = {};
   bool dirty[FNP_MAT_COUNT] = {};

@@ -43,10 +43,18 @@ __device__ __forceinline__ void epilogue(const EpiCheb &e, int r, double s) {
   e.out[r] = v;
 }
 
+// x is addressed as [owned entries | ghost buffer]: column c < nown reads the caller's
+// vector, c >= nown reads the halo buffer filled by the exchange (dist.cu).  Single-GPU
+// contexts pass nown = INT_MAX.
+__device__ __forceinline__ double gather_x(const double *__restrict__ x, const double *__restrict__ xg, int nown, int c) {
+  return c < nown ? __ldg(x + c) : __ldg(xg + (c - nown));
+}
+
 template <int LANES, class Epi>
 __global__ void __launch_bounds__(256)
 spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-            const double *__restrict__ val, const double *__restrict__ x, Epi epi) {
+            const double *__restrict__ val, const double *__restrict__ x, const double *__restrict__ xg, int nown,
+            Epi epi) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = tid / LANES;
   const int lane = tid % LANES;
@@ -57,10 +65,10 @@ spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__rest
     for (; k + LANES < end; k += 2 * LANES) {
       const int c0 = __ldg(col + k), c1 = __ldg(col + k + LANES);
       const double v0 = __ldg(val + k), v1 = __ldg(val + k + LANES);
-      s0 += v0 * __ldg(x + c0);
-      s1 += v1 * __ldg(x + c1);
+      s0 += v0 * gather_x(x, xg, nown, c0);
+      s1 += v1 * gather_x(x, xg, nown, c1);
     }
-    if (k < end) s0 += __ldg(val + k) * __ldg(x + __ldg(col + k));
+    if (k < end) s0 += __ldg(val + k) * gather_x(x, xg, nown, __ldg(col + k));
   }
   double s = s0 + s1;
 #pragma unroll
@@ -93,7 +101,7 @@ template <class Epi>
 __global__ void __launch_bounds__(256)
 spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t *__restrict__ col,
                  const double *__restrict__ val, const int32_t *__restrict__ perm, const double *__restrict__ x,
-                 Epi epi) {
+                 const double *__restrict__ xg, int nown, Epi epi) {
   const int slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (slice >= nslices) return;
@@ -109,12 +117,12 @@ spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t 
     const int c2 = __ldcs(cp + (k + 2) * SELL_C), c3 = __ldcs(cp + (k + 3) * SELL_C);
     const double v0 = __ldcs(vp + (k + 0) * SELL_C), v1 = __ldcs(vp + (k + 1) * SELL_C);
     const double v2 = __ldcs(vp + (k + 2) * SELL_C), v3 = __ldcs(vp + (k + 3) * SELL_C);
-    s0 += v0 * __ldg(x + c0);
-    s1 += v1 * __ldg(x + c1);
-    s2 += v2 * __ldg(x + c2);
-    s3 += v3 * __ldg(x + c3);
+    s0 += v0 * gather_x(x, xg, nown, c0);
+    s1 += v1 * gather_x(x, xg, nown, c1);
+    s2 += v2 * gather_x(x, xg, nown, c2);
+    s3 += v3 * gather_x(x, xg, nown, c3);
   }
-  for (; k < len; ++k) s0 += __ldcs(vp + k * SELL_C) * __ldg(x + __ldcs(cp + k * SELL_C));
+  for (; k < len; ++k) s0 += __ldcs(vp + k * SELL_C) * gather_x(x, xg, nown, __ldcs(cp + k * SELL_C));
   if (row >= 0) epilogue(epi, row, (s0 + s1) + (s2 + s3));
 }
 
@@ -241,22 +249,30 @@ void csr_set_values(Ctx &c, DevCsr &A, const HostCsr &h, const double *val, bool
 template <class Epi>
 static void spmv_launch(Ctx &c, const DevCsr &A, const double *x, const Epi &epi) {
   if (A.nrows == 0) return;
+  // multi-rank: fetch the ghost entries of x from their owners first
+  const double *xg = nullptr;
+  int nown = INT32_MAX;
+  if (A.halo) {
+    halo_exchange(c, *A.halo, x);
+    xg = A.halo->ghost.p;
+    nown = A.ncols_own;
+  }
   StageTimer kt(c, "spmv " + A.tag, 2);
   if (A.sell) {
     const int threads = 256;
     const int grid = (int)(((int64_t)A.nslices * 32 + threads - 1) / threads);
-    spmv_sell_kernel<Epi><<<grid, threads, 0, c.stream>>>(A.nslices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p, A.sl_perm.p, x, epi);
+    spmv_sell_kernel<Epi><<<grid, threads, 0, c.stream>>>(A.nslices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p, A.sl_perm.p, x, xg, nown, epi);
     FNP_LAUNCH_CHECK(c);
     return;
   }
   const int threads = 256;
   auto grid = [&](int lanes) { return (int)(((int64_t)A.nrows * lanes + threads - 1) / threads); };
   switch (A.lanes) {
-    case 2: spmv_kernel<2, Epi><<<grid(2), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, epi); break;
-    case 4: spmv_kernel<4, Epi><<<grid(4), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, epi); break;
-    case 8: spmv_kernel<8, Epi><<<grid(8), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, epi); break;
-    case 16: spmv_kernel<16, Epi><<<grid(16), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, epi); break;
-    default: spmv_kernel<32, Epi><<<grid(32), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, epi); break;
+    case 2: spmv_kernel<2, Epi><<<grid(2), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); break;
+    case 4: spmv_kernel<4, Epi><<<grid(4), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); break;
+    case 8: spmv_kernel<8, Epi><<<grid(8), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); break;
+    case 16: spmv_kernel<16, Epi><<<grid(16), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); break;
+    default: spmv_kernel<32, Epi><<<grid(32), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); break;
   }
   FNP_LAUNCH_CHECK(c);
 }
@@ -502,19 +518,19 @@ void vec_scale_inv_sqrt(Ctx &c, int64_t n, const double *nrm2_dev, const double 
 
 // x = Minv b, Minv dense row-major n x n: one warp per row
 __global__ void __launch_bounds__(256)
-gemv_kernel(int n, const double *__restrict__ M, const double *__restrict__ b, double *__restrict__ x) {
+gemv_kernel(int nrows, int n, const double *__restrict__ M, const double *__restrict__ b, double *__restrict__ x) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (row >= n) return;
+  if (row >= nrows) return;
   double s = 0.0;
   for (int k = lane; k < n; k += 32) s += M[(int64_t)row * n + k] * __ldg(b + k);
   s = warp_sum(s);
   if (lane == 0) x[row] = s;
 }
 
-void dense_gemv(Ctx &c, int n, const double *Minv, const double *b, double *x) {
-  if (n <= 0) return;
-  gemv_kernel<<<(n * 32 + 255) / 256, 256, 0, c.stream>>>(n, Minv, b, x);
+void dense_gemv(Ctx &c, int nrows, int ncols, const double *Minv, const double *b, double *x) {
+  if (nrows <= 0) return;
+  gemv_kernel<<<(nrows * 32 + 255) / 256, 256, 0, c.stream>>>(nrows, ncols, Minv, b, x);
   FNP_LAUNCH_CHECK(c);
 }
 

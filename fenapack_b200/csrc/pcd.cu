@@ -27,6 +27,10 @@ __global__ void cg_p_kernel(int64_t n, const double *__restrict__ rz_new, const 
     p[i] = z[i] + beta * p[i];
 }
 
+static void allreduce1(Ctx &c, double *dev) {
+  if (c.nranks > 1) FNP_NCCL(nccl().AllReduce(dev, dev, 1, ncclDouble, ncclSum, c.comm, c.stream));
+}
+
 static void apply_inner_pc(Ctx &c, const InnerOpts &o, const DevCsr &A, DevHierarchy *H, const double *r, double *z) {
   if (o.pc == PC_AMG) {
     amg_vcycle(c, *H, r, z);
@@ -68,15 +72,18 @@ static void inner_solve(Ctx &c, const InnerOpts &o, const DevCsr &A, DevHierarch
       apply_inner_pc(c, o, A, H, r, z);
       vec_copy(c, n, z, p);
       dot(c, n, r, z, rz);
+      allreduce1(c, rz);
       const int nb = 148 * 8;
       for (int k = 0; k < o.max_it; ++k) {
         spmv_store(c, A, p, q);
         dot(c, n, p, q, pq);
+        allreduce1(c, pq);
         cg_xr_kernel<<<nb, 256, 0, c.stream>>>(n, rz, pq, p, q, x, r);
         c.launches++;
         if (k + 1 == o.max_it) break;
         apply_inner_pc(c, o, A, H, r, z);
         dot(c, n, r, z, rz2);
+        allreduce1(c, rz2);
         cg_p_kernel<<<nb, 256, 0, c.stream>>>(n, rz2, rz, z, p);
         c.launches++;
         std::swap(rz, rz2);
@@ -169,7 +176,8 @@ void system_matvec(Ctx &c, const double *x, double *y) {
 // ---------------------------------------------------------------------------
 static void build_amg(Ctx &c, int which, DevHierarchy &H, const AmgParams &p) {
   H.params = p;
-  amg_build_host(c.hmat[which], p, H.host);
+  const bool is_u = which == FNP_MAT_A00 || which == FNP_MAT_P00;
+  amg_build_host(c, c.hmat[which], is_u ? c.u_begins : c.p_begins, p, H.host);
   amg_upload(c, H, which == FNP_MAT_AP ? "Ap" : "A00", &c.dmat[which]);
 }
 

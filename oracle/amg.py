@@ -14,8 +14,11 @@ V-cycle can be checked to rounding:
                rows without strong neighbours (Dirichlet rows) stay un-aggregated
   tentative    T[i, agg(i)] = 1/sqrt(|agg|)
   prolongator  P = (I - (4/3)/rho * D^-1 A) T, rho = power-iteration estimate of
-               rho(D^-1 A) (20 steps, fixed start vector) times 1.1
-  coarse op    A_c = P^T A P
+               rho(D^-1 A) (20 steps, fixed start vector) times 1.1; entries below
+               p_trunc * max|row| are dropped and rows rescaled to their row sum
+  coarse op    A_c = P^T A P, then entries below coarse_drop*sqrt(|a_ii||a_jj|) are
+               lumped onto the diagonal (SA coarse stencils of P2 operators in 3D
+               have ~200 entries per row, ~90 % of them negligible)
   smoother     Chebyshev-Jacobi of ``smooth_steps`` steps on [rho/ratio, rho] (one
                step = damped Jacobi), same recurrence as the Mp solve
   coarsest     dense inverse
@@ -159,32 +162,107 @@ class Hierarchy:
         return self.vcycle(b)
 
 
+def filter_lumped(A, drop):
+    """Sparsify a coarse operator: off-diagonal entries with
+    |a_ij| < drop * sqrt(|a_ii| |a_jj|) are removed and added to the diagonal of
+    their row (row sums, hence the action on constants, are preserved)."""
+    if drop <= 0.0:
+        return A
+    A = A.tocsr()
+    d = np.abs(A.diagonal())
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    cols = A.indices
+    small = (rows != cols) & (np.abs(A.data) < drop * np.sqrt(d[rows] * d[cols]))
+    lump = np.bincount(rows[small], weights=A.data[small], minlength=A.shape[0])
+    data = A.data + np.where(rows == cols, lump[rows], 0.0)
+    keep = ~small
+    out = sp.csr_matrix((data[keep], (rows[keep], cols[keep])), shape=A.shape)
+    out.sort_indices()
+    return out
+
+
+def truncate_prolongator(P, trunc):
+    """Drop entries below trunc * max|row| and rescale every row to its former row
+    sum (constants stay in the range of P)."""
+    if trunc <= 0.0:
+        return P
+    n = P.shape[0]
+    rows = np.repeat(np.arange(n), np.diff(P.indptr))
+    rmax = np.zeros(n)
+    np.maximum.at(rmax, rows, np.abs(P.data))
+    rs0 = np.bincount(rows, weights=P.data, minlength=n)
+    keep = np.abs(P.data) >= trunc * rmax[rows]
+    rs1 = np.bincount(rows[keep], weights=P.data[keep], minlength=n)
+    scale = np.where(rs1 != 0.0, rs0 / np.where(rs1 != 0.0, rs1, 1.0), 1.0)
+    out = sp.csr_matrix((scale[rows[keep]] * P.data[keep], (rows[keep], P.indices[keep])), shape=P.shape)
+    out.sort_indices()
+    return out
+
+
+def _block_of(begins, n):
+    """Block (rank) index of every row for ownership offsets ``begins``."""
+    return np.searchsorted(np.asarray(begins[1:]), np.arange(n), side="right")
+
+
 def build_hierarchy(A, theta=0.08, max_levels=12, coarse_size=400, smooth_steps=2,
-                    eig_ratio=10.0, omega_scale=4.0 / 3.0):
+                    eig_ratio=10.0, omega_scale=4.0 / 3.0, coarse_drop=0.0, p_trunc=0.2, blocks=None):
+    """``blocks``: ownership offsets [0, n_1, ..., n] of a row partition.  With more
+    than one block the aggregation and the prolongator smoothing are block local
+    (no aggregate crosses a block boundary, P = T - omega D^-1 A_bd T with A_bd the
+    block-diagonal part), exactly what the multi-rank library does; the Galerkin
+    product uses the full A.  One block = the plain serial algorithm."""
     H = Hierarchy(smooth_steps=smooth_steps, eig_ratio=eig_ratio)
     A = sp.csr_matrix(A)
     A.sort_indices()
+    begins = [0, A.shape[0]] if blocks is None else [int(b) for b in blocks]
+    H.begins = []
     while True:
+        n = A.shape[0]
+        nb = len(begins) - 1
         diag = A.diagonal()
         dinv = np.where(diag != 0.0, 1.0 / np.where(diag != 0.0, diag, 1.0), 0.0)
-        rho = estimate_rho(A, dinv)
+        if nb == 1:
+            Abd = A
+            rho = estimate_rho(A, dinv)
+        else:
+            blk = _block_of(begins, n)
+            coo = A.tocoo()
+            same = blk[coo.row] == blk[coo.col]
+            Abd = sp.csr_matrix((coo.data[same], (coo.row[same], coo.col[same])), shape=A.shape)
+            Abd.sort_indices()
+            rho = max(estimate_rho(Abd[b0:b1, b0:b1].tocsr(), dinv[b0:b1])
+                      for b0, b1 in zip(begins[:-1], begins[1:]) if b1 > b0)
         lvl = Level(A=A, dinv=dinv, rho=rho)
         H.levels.append(lvl)
-        if A.shape[0] <= coarse_size or len(H.levels) >= max_levels:
+        H.begins.append(list(begins))
+        if n <= coarse_size or len(H.levels) >= max_levels:
             break
-        S = strength_graph(A, theta * 0.5 ** (len(H.levels) - 1))
-        agg, nagg = aggregate_greedy(S)
-        if nagg == 0 or nagg >= A.shape[0]:
+        S = strength_graph(Abd, theta * 0.5 ** (len(H.levels) - 1))
+        if nb == 1:
+            agg, nagg = aggregate_greedy(S)
+            cbegins = [0, nagg]
+        else:
+            agg = np.full(n, -1, dtype=np.int64)
+            cbegins = [0]
+            for b0, b1 in zip(begins[:-1], begins[1:]):
+                a, na = aggregate_greedy(S[b0:b1, b0:b1].tocsr())
+                agg[b0:b1] = np.where(a >= 0, a + cbegins[-1], -1)
+                cbegins.append(cbegins[-1] + na)
+            nagg = cbegins[-1]
+        if nagg == 0 or nagg >= n:
             break
         T = tentative_prolongator(agg, nagg)
         omega = omega_scale / rho
-        P = (T - omega * (sp.diags(dinv) @ (A @ T))).tocsr()
+        P = (T - omega * (sp.diags(dinv) @ (Abd @ T))).tocsr()
         P.sort_indices()
+        P = truncate_prolongator(P, p_trunc)
         R = P.T.tocsr()
         R.sort_indices()
         Ac = (R @ (A @ P)).tocsr()
         Ac.sort_indices()
+        Ac = filter_lumped(Ac, coarse_drop)
         lvl.P, lvl.R = P, R
         A = Ac
+        begins = cbegins
     H.coarse_inv = np.linalg.inv(H.levels[-1].A.toarray())
     return H

@@ -1,0 +1,92 @@
+"""Multi-rank worker (one process per GPU, launched by torchrun from
+tests/test_dist_gpu.py): row-partitioned operators, halo exchange, distributed AMG
+and FGMRES through the C ABI, checked against the serial oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from fenapack_b200 import capi  # noqa: E402
+from oracle import amg as oamg  # noqa: E402
+from oracle import petsc_algos as pa  # noqa: E402
+from oracle import problems  # noqa: E402
+from util import ITERATIVE_OPTIONS, relerr  # noqa: E402
+
+
+def split(n, world, align=1):
+    b = [((n // align) * r // world) * align for r in range(world)] + [n]
+    return b
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    variant = sys.argv[1] if len(sys.argv) > 1 else "BRM1"
+    prob, _ = problems.channel(12, 4, 6, variant=variant) if variant == "BRM1" else problems.lid_driven_cavity(8, dim=3, variant="BRM2")
+    ub, pb = split(prob.n_u, world, 3), split(prob.n_p, world)
+    u0, u1, p0, p1 = ub[rank], ub[rank + 1], pb[rank], pb[rank + 1]
+
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx = capi.Context(local, nccl_id=idt.cpu().numpy().tobytes(), rank=rank, nranks=world)
+    opts = dict(ITERATIVE_OPTIONS)
+    opts["fieldsplit_p_pc_python_type"] = "fenapack.PCDPC_" + prob.variant
+    opts["fieldsplit_p_PCD_Mp_ksp_chebyshev_eigenvalues"] = "%r, %r" % tuple(prob.cheb_bounds)
+    ctx.set_options(opts)
+    ctx.set_layout(u1 - u0, p1 - p0, u0, prob.n_u, p0, prob.n_p)
+    P00 = prob.P00 if prob.P00 is not None else prob.A00
+    mats = {capi.MAT_A00: (prob.A00, u0, u1), capi.MAT_A01: (prob.A01, u0, u1), capi.MAT_A10: (prob.A10, p0, p1),
+            capi.MAT_AP: (prob.Ap, p0, p1), capi.MAT_MP: (prob.Mp, p0, p1), capi.MAT_KP: (prob.Kp, p0, p1)}
+    if prob.P00 is not None:
+        mats[capi.MAT_P00] = (prob.P00, u0, u1)
+    for which, (A, r0, r1) in mats.items():
+        ctx.set_matrix(which, A[r0:r1, :].tocsr())
+    sel = (prob.bc_idx >= p0) & (prob.bc_idx < p1)
+    ctx.set_bc(prob.bc_idx[sel] - p0, prob.bc_val[sel])
+    ctx.setup()
+
+    rng = np.random.default_rng(0)
+    # distributed SpMV of every operator
+    for which, (A, r0, r1) in mats.items():
+        x = rng.standard_normal(A.shape[1])
+        c0, c1 = (u0, u1) if A.shape[1] == prob.n_u else (p0, p1)
+        y = ctx.spmv(which, x[c0:c1], r1 - r0)
+        assert relerr(y, (A @ x)[r0:r1]) <= 1e-12, ("spmv", which)
+    # the preconditioner against the oracle with the same block-local hierarchy
+    Hu = oamg.build_hierarchy(P00, blocks=ub)
+    Hp = oamg.build_hierarchy(prob.Ap, blocks=pb)
+    pc = pa.PCDPreconditioner(prob, "iterative", amg_u=Hu, amg_p=Hp)
+    b = rng.standard_normal(prob.n_p)
+    assert relerr(ctx.ap_solve(b[p0:p1]), pc.solve_Ap(b)[p0:p1]) <= 1e-9, "ap_solve"
+    bu = rng.standard_normal(prob.n_u)
+    assert relerr(ctx.u_solve(bu[u0:u1]), pc.solve_A00(bu)[u0:u1]) <= 1e-9, "u_solve"
+    xu, xp = rng.standard_normal(prob.n_u), rng.standard_normal(prob.n_p)
+    yu, yp = ctx.pc_apply(xu[u0:u1], xp[p0:p1])
+    ru, rp = pc.apply_split(xu, xp)
+    assert relerr(yp, rp[p0:p1]) <= 1e-8 and relerr(yu, ru[u0:u1]) <= 1e-8, "pc_apply"
+    # the outer solve
+    A, rhs = prob.system_matrix(), prob.rhs()
+    x_ref, its_ref, hist_ref, _ = pa.fgmres(A, pc, rhs, rtol=1e-6, restart=150)
+    su, sp_, its, rn, nap = ctx.solve(prob.b_u[u0:u1], prob.b_p[p0:p1])
+    assert abs(its - its_ref) <= 1, (its, its_ref)
+    xs = np.concatenate([x_ref[:prob.n_u][u0:u1], x_ref[prob.n_u:][p0:p1]])
+    assert relerr(np.concatenate([su, sp_]), xs) <= 1e-5
+    dist.barrier()
+    if rank == 0:
+        print(f"DIST OK world={world} variant={prob.variant} its={its} oracle_its={its_ref}")
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

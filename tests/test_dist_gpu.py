@@ -1,0 +1,28 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): launches
+tests/dist_worker.py with torchrun, one process per GPU."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["BRM1", "BRM2"])
+def test_two_rank_parity(variant):
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "dist_worker.py"), variant]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DIST OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -236,3 +236,22 @@ def test_spmv_ragged_and_empty_rows(kernel):
         ctx.set_values(capi.MAT_KP, A2.data)
         assert relerr(ctx.spmv(capi.MAT_KP, x, n), A2 @ x) <= TOL_SPMV
         ctx.close()
+
+
+def test_amg_coarse_drop_option_matches_oracle():
+    """pc_amg_coarse_drop (lumped sparsification of the Galerkin operators): same
+    hierarchy as the oracle's filter_lumped, V-cycle parity on it."""
+    prob, _ = problems.lid_driven_cavity(8, dim=3, variant="BRM2")
+    ctx = make_context(prob, {"fieldsplit_u_pc_amg_coarse_drop": 0.02, "fieldsplit_p_PCD_Ap_pc_amg_coarse_drop": 0.02})
+    A = prob.P00 if prob.P00 is not None else prob.A00
+    levels, cinv = ctx.amg_hierarchy(capi.MAT_A00)
+    H = oamg.build_hierarchy(A, coarse_drop=0.02)
+    H0 = oamg.build_hierarchy(A, coarse_drop=0.0)
+    assert [l["A"].shape[0] for l in levels] == [l.A.shape[0] for l in H.levels]
+    assert sum(l["A"].nnz for l in levels[1:]) < 0.5 * sum(l.A.nnz for l in H0.levels[1:])
+    for dl, ol in zip(levels, H.levels):
+        assert dl["A"].nnz == ol.A.nnz and abs(dl["A"] - ol.A).max() <= 1e-10 * abs(ol.A).max()
+    Hd = oracle_hierarchy_from_device(ctx, capi.MAT_A00)
+    b = np.random.default_rng(2).standard_normal(prob.n_u)
+    assert relerr(ctx.amg_vcycle(capi.MAT_A00, b), Hd.vcycle(b)) <= 1e-11
+    ctx.close()
