@@ -18,10 +18,23 @@ TOL_SPMV = 1e-12
 TOL_PC = 1e-8
 
 
-@pytest.fixture(scope="module", params=["bfs_BRM1", "bfs_BRM2", "cavity3d_BRM2", "channel3d_BRM1"])
+@pytest.fixture(scope="module", params=["bfs_BRM1", "bfs_BRM2", "cavity3d_BRM2", "channel3d_BRM1",
+                                        "cavity2d_BRM2", "bfs_unsteady_BRM1", "cavity3d_newton_BRM2"])
 def case(request):
+    """Reduced-size versions of the BASELINE.json configs: cfg1 (BFS), cfg2 (2D cavity,
+    BRM2), cfg3 (unsteady BFS: reaction term 1/dt in A00 and Kp), cfg4 (3D channel,
+    BRM1), cfg5 (3D cavity, BRM2; Picard and Newton coupling)."""
     name = request.param
-    if name.startswith("bfs"):
+    if name == "cavity2d_BRM2":
+        prob, _ = problems.lid_driven_cavity(24, dim=2, variant="BRM2")
+    elif name == "bfs_unsteady_BRM1":
+        p0, space = problems.backward_facing_step(3, variant="BRM1", idt=5.0)
+        x = pa.direct_solver(p0.system_matrix())(p0.rhs())
+        prob, _ = problems.backward_facing_step(3, variant="BRM1", wind=x[:p0.n_u].reshape(-1, 2), idt=5.0,
+                                                stabilise=True)
+    elif name == "cavity3d_newton_BRM2":
+        prob, _ = problems.lid_driven_cavity(6, dim=3, variant="BRM2", newton=True)
+    elif name.startswith("bfs"):
         variant = name.split("_")[1]
         # a Picard step around a non-trivial wind (the Stokes solution)
         p0, space = problems.backward_facing_step(3, variant=variant)
