@@ -59,7 +59,7 @@ void cheb_jacobi(Ctx &c, const DevCsr &A, const double *b, double emin, double e
 
 static void upload_csr(Ctx &c, const HostCsr &h, DevCsr &d, const std::string &tag,
                        std::shared_ptr<HaloPlan> halo = nullptr, int64_t n_own = -1) {
-  csr_upload_pattern(c, d, h, tag);
+  csr_upload_pattern(c, d, h, tag, (halo && c.overlap) ? n_own : -1);
   csr_set_values(c, d, h, h.val.data(), false);
   if (halo) {
     d.halo = halo;

@@ -41,6 +41,10 @@ Ctx::Ctx(int dev) : device(dev) {
 Ctx::~Ctx() {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
+  drop_graph();
+  if (comm_stream) { cudaStreamSynchronize(comm_stream); cudaStreamDestroy(comm_stream); }
+  if (ev_x) cudaEventDestroy(ev_x);
+  if (ev_halo) cudaEventDestroy(ev_halo);
   if (comm) nccl().CommDestroy(comm);
   if (pinned) cudaFreeHost(pinned);
   for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -167,6 +171,7 @@ static void set_inner_option(InnerOpts &o, const std::string &full, const std::s
 }
 
 static void set_option(Ctx &c, const std::string &name, const std::string &v) {
+  if (name.rfind("fnp_", 0) != 0) c.drop_graph();      // solver options are baked into the captured apply
   const std::string pu = "fieldsplit_u_", pap = "fieldsplit_p_PCD_Ap_", pmp = "fieldsplit_p_PCD_Mp_";
   if (starts_with(name, pap)) return set_inner_option(c.opt_ap, name, name.substr(pap.size()), v);
   if (starts_with(name, pmp)) return set_inner_option(c.opt_mp, name, name.substr(pmp.size()), v);
@@ -194,6 +199,11 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
     else if (v == "csr") c.spmv_mode = 1;
     else if (v == "sell") c.spmv_mode = 2;
     else throw Error(FNP_ERR_OPTION, "option fnp_spmv_kernel: auto | csr | sell (takes effect at fnp_set_pattern)");
+  } else if (name == "fnp_halo_overlap") {
+    c.overlap = parse_int(name, v);
+  } else if (name == "fnp_cuda_graph") {
+    c.use_graph = parse_int(name, v);
+    c.drop_graph();
   } else if (name == "fnp_timers") {
     c.timers_on = parse_int(name, v);
   } else {
@@ -260,7 +270,8 @@ static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t 
     const std::vector<int64_t> &begins = u_cols ? c.u_begins : c.p_begins;
     HostCsr loc = h;
     std::shared_ptr<HaloPlan> plan = build_halo(c, loc, begins, nullptr);
-    csr_upload_pattern(c, d, loc, names[which]);
+    const int64_t n_own_cols = begins[c.rank + 1] - begins[c.rank];
+    csr_upload_pattern(c, d, loc, names[which], c.overlap ? n_own_cols : -1);
     d.halo = plan;
     d.ncols_own = (int32_t)(begins[c.rank + 1] - begins[c.rank]);
     d.nghost = plan ? plan->nghost : 0;
@@ -399,6 +410,11 @@ int fnp_create_dist(fnp_context **out, int device, const void *nccl_id, int rank
   FNP_NCCL(nccl().CommInitRank(&ctx->c.comm, nranks, id, rank));
   ctx->c.rank = rank;
   ctx->c.nranks = nranks;
+  if (nranks > 1) {
+    FNP_CUDA(cudaStreamCreateWithFlags(&ctx->c.comm_stream, cudaStreamNonBlocking));
+    FNP_CUDA(cudaEventCreateWithFlags(&ctx->c.ev_x, cudaEventDisableTiming));
+    FNP_CUDA(cudaEventCreateWithFlags(&ctx->c.ev_halo, cudaEventDisableTiming));
+  }
   *out = ctx.release();
   FNP_API_END
 }

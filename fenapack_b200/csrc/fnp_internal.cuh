@@ -117,7 +117,7 @@ struct HaloPlan {
   DevBuf<int32_t> send_idx;
   DevBuf<double> send_buf, ghost;
 };
-void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own);
+void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own, cudaStream_t stream);
 
 // Device-resident CSR operator; columns index [x_own | x_ghost].
 struct DevCsr {
@@ -133,9 +133,9 @@ struct DevCsr {
   // SELL-32-sigma copy (short-row operators): slice s holds rows sl_perm[32 s .. 32 s + 31],
   // entries stored column-major inside the slice, padded to the slice's longest row
   bool sell = false;
-  int32_t nslices = 0;
-  int64_t sell_entries = 0;  // padded entry count
-  DevBuf<int32_t> sl_ptr, sl_col, sl_perm;
+  int32_t nslices = 0, nslices_b = 0;       // interior part / boundary part (rows with ghost columns)
+  int64_t sell_entries = 0, sell_entries_a = 0;   // padded entry count: total / interior part
+  DevBuf<int32_t> sl_ptr, sl_col, sl_perm, sl_ptr_b, sl_perm_b;
   DevBuf<double> sl_val;
   std::vector<int32_t> sell_pos;   // host: CSR entry k -> position in sl_val (for value refreshes)
   bool has_dinv = false;
@@ -164,7 +164,7 @@ struct EpiCheb {             // out = add + c0 p0 + c1 p1 + c2 dinv (b - A p1)  
 // Upload one operator: picks the storage format from the row-length histogram
 // (SELL-32-sigma for short rows, CSR + sub-warp-per-row kernel for long rows).
 // `val` may be null (pattern only); csr_set_values refreshes the numbers later.
-void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag);
+void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag, int64_t n_own_split = -1);
 void csr_set_values(Ctx &c, DevCsr &A, const HostCsr &pattern, const double *val, bool want_dinv);
 void spmv_store(Ctx &c, const DevCsr &A, const double *x, double *y);
 void spmv_axpby(Ctx &c, const DevCsr &A, const double *x, double a, double b, const double *z, double *y);
@@ -288,6 +288,8 @@ struct Ctx {
   // distributed
   int rank = 0, nranks = 1;
   ncclComm_t comm = nullptr;
+  cudaStream_t comm_stream = nullptr;      // halo exchanges overlap the interior rows
+  cudaEvent_t ev_x = nullptr, ev_halo = nullptr;
 
   std::vector<int64_t> u_begins, p_begins;   // ownership offsets of all ranks
 
@@ -332,6 +334,15 @@ struct Ctx {
   size_t pinned_n = 0;
   DevBuf<double> io[4];       // staging for host-pointer calls
 
+  // CUDA graph of one block-triangular PC apply on fixed staging buffers (single-rank
+  // contexts): ~500 short launches per apply collapse into one graph launch
+  int overlap = 1;              // split SELL operators into interior/boundary rows and overlap the halo exchange
+  int use_graph = 1;
+  cudaGraphExec_t pc_graph = nullptr;
+  int64_t pc_graph_nodes = 0;
+  DevBuf<double> g_in, g_out;
+  void drop_graph();
+
   // Krylov basis
   std::vector<DevBuf<double>> V, Z;
   DevBuf<double> kr_w, kr_x, kr_b;
@@ -368,6 +379,8 @@ void ap_solve(Ctx &c, const double *b, double *x);
 void u_solve(Ctx &c, const double *b, double *x);
 void schur_apply(Ctx &c, const double *x_p, double *y_p);
 void pc_apply(Ctx &c, const double *x_u, const double *x_p, double *y_u, double *y_p);
+// same on split vectors [u;p], replayed from a captured CUDA graph when possible
+void pc_apply_vec(Ctx &c, const double *x, double *y);
 void system_matvec(Ctx &c, const double *x, double *y);   // split vectors [u;p]
 void solve_fgmres(Ctx &c, const double *b, double *x, int32_t *its, double *rnorm, int32_t *napply);
 

@@ -101,7 +101,7 @@ void solve_fgmres(Ctx &c, const double *b, double *x, int32_t *its_out, double *
         zj = c.kr_x.p;
       }
       // z = M^-1 v_j ; w = A z
-      pc_apply(c, V[j], V[j] + c.n_u, zj, zj + c.n_u);
+      pc_apply_vec(c, V[j], zj);
       ++napply;
       system_matvec(c, zj, w);
       // classical Gram-Schmidt
@@ -155,7 +155,7 @@ void solve_fgmres(Ctx &c, const double *b, double *x, int32_t *its_out, double *
       c.kr_b.ensure((size_t)n);
       vec_zero(c, n, c.kr_b.p);
       multi_axpy_ptrs(c, n, V.ptrs.p, jdone, ydev, c.kr_b.p);
-      pc_apply(c, c.kr_b.p, c.kr_b.p + c.n_u, c.kr_x.p, c.kr_x.p + c.n_u);
+      pc_apply_vec(c, c.kr_b.p, c.kr_x.p);
       ++napply;
       vec_axpy(c, n, 1.0, c.kr_x.p, x);
     }

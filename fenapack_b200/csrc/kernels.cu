@@ -132,21 +132,22 @@ static int pick_lanes(double mean_row) {
   return lanes;
 }
 
-// Build the SELL-32-sigma layout of a pattern: permutation, slice pointers, padded
-// column array and the CSR->SELL position map (kept on the host for value refreshes).
-static void build_sell(Ctx &c, DevCsr &A, const HostCsr &h) {
-  const int64_t n = h.nrows;
+// SELL-32-sigma layout of a subset of rows: permutation (padded with -1 to whole slices),
+// slice pointers relative to `base`, and the entry count.
+static void sell_layout(const HostCsr &h, const std::vector<int32_t> &rows, std::vector<int32_t> &perm,
+                        std::vector<int32_t> &ptr, int64_t &total) {
+  const int64_t n = (int64_t)rows.size();
   const int64_t nsl = (n + SELL_C - 1) / SELL_C;
-  std::vector<int32_t> perm((size_t)nsl * SELL_C, -1);
+  perm.assign((size_t)nsl * SELL_C, -1);
   for (int64_t w0 = 0; w0 < n; w0 += SELL_SIGMA) {
     const int64_t w1 = std::min<int64_t>(n, w0 + SELL_SIGMA);
-    for (int64_t i = w0; i < w1; ++i) perm[i] = (int32_t)i;
+    for (int64_t i = w0; i < w1; ++i) perm[i] = rows[i];
     std::stable_sort(perm.begin() + w0, perm.begin() + w1, [&](int32_t a, int32_t b) {
       return h.rowptr[a + 1] - h.rowptr[a] > h.rowptr[b + 1] - h.rowptr[b];
     });
   }
-  std::vector<int32_t> ptr(nsl + 1, 0);
-  int64_t total = 0;
+  ptr.assign(nsl + 1, 0);
+  total = 0;
   for (int64_t s = 0; s < nsl; ++s) {
     int32_t len = 0;
     for (int l = 0; l < SELL_C; ++l) {
@@ -157,38 +158,69 @@ static void build_sell(Ctx &c, DevCsr &A, const HostCsr &h) {
     FNP_REQUIRE(total < (int64_t)INT32_MAX, FNP_ERR_ARG, "SELL layout exceeds 2^31 entries on one rank");
     ptr[s + 1] = (int32_t)total;
   }
-  std::vector<int32_t> col((size_t)total);
-  A.sell_pos.assign((size_t)h.nnz(), 0);
+}
+
+static void sell_fill(const HostCsr &h, const std::vector<int32_t> &perm, const std::vector<int32_t> &ptr, int64_t base,
+                      std::vector<int32_t> &col, std::vector<int32_t> &pos) {
+  const int64_t nsl = (int64_t)ptr.size() - 1;
 #pragma omp parallel for schedule(static)
   for (int64_t s = 0; s < nsl; ++s) {
-    const int32_t base = ptr[s];
-    const int32_t len = (ptr[s + 1] - base) / SELL_C;
+    const int64_t sbase = base + ptr[s];
+    const int32_t len = (ptr[s + 1] - ptr[s]) / SELL_C;
     for (int l = 0; l < SELL_C; ++l) {
       const int32_t r = perm[s * SELL_C + l];
       const int32_t b = r >= 0 ? h.rowptr[r] : 0, e = r >= 0 ? h.rowptr[r + 1] : 0;
       const int32_t fill = e > b ? h.col[b] : 0;       // padding: zero value, harmless in-range column
       for (int32_t k = 0; k < len; ++k) {
-        const int32_t dst = base + k * SELL_C + l;
+        const int64_t dst = sbase + (int64_t)k * SELL_C + l;
         if (b + k < e) {
           col[dst] = h.col[b + k];
-          A.sell_pos[b + k] = dst;
+          pos[b + k] = (int32_t)dst;
         } else {
           col[dst] = fill;
         }
       }
     }
   }
-  A.nslices = (int32_t)nsl;
-  A.sell_entries = total;
-  A.sl_ptr.upload(ptr.data(), ptr.size(), c.stream);
-  A.sl_perm.upload(perm.data(), perm.size(), c.stream);
+}
+
+// Build the SELL copy of a pattern.  With n_own_split >= 0 (multi-rank) the rows are split
+// into an interior part (no ghost column) and a boundary part, so that the interior part
+// can run while the halo exchange is in flight.
+static void build_sell(Ctx &c, DevCsr &A, const HostCsr &h, int64_t n_own_split) {
+  std::vector<int32_t> rows_a, rows_b;
+  rows_a.reserve(h.nrows);
+  for (int64_t i = 0; i < h.nrows; ++i) {
+    bool ghost = false;
+    if (n_own_split >= 0)
+      for (int32_t k = h.rowptr[i]; k < h.rowptr[i + 1]; ++k)
+        if (h.col[k] >= n_own_split) { ghost = true; break; }
+    (ghost ? rows_b : rows_a).push_back((int32_t)i);
+  }
+  std::vector<int32_t> perm_a, ptr_a, perm_b, ptr_b;
+  int64_t tot_a = 0, tot_b = 0;
+  sell_layout(h, rows_a, perm_a, ptr_a, tot_a);
+  sell_layout(h, rows_b, perm_b, ptr_b, tot_b);
+  FNP_REQUIRE(tot_a + tot_b < (int64_t)INT32_MAX, FNP_ERR_ARG, "SELL layout exceeds 2^31 entries on one rank");
+  std::vector<int32_t> col((size_t)(tot_a + tot_b));
+  A.sell_pos.assign((size_t)h.nnz(), 0);
+  sell_fill(h, perm_a, ptr_a, 0, col, A.sell_pos);
+  sell_fill(h, perm_b, ptr_b, tot_a, col, A.sell_pos);
+  A.nslices = (int32_t)ptr_a.size() - 1;
+  A.nslices_b = (int32_t)ptr_b.size() - 1;
+  A.sell_entries = tot_a + tot_b;
+  A.sell_entries_a = tot_a;
+  A.sl_ptr.upload(ptr_a.data(), ptr_a.size(), c.stream);
+  A.sl_perm.upload(perm_a.data(), perm_a.size(), c.stream);
+  A.sl_ptr_b.upload(ptr_b.data(), ptr_b.size(), c.stream);
+  A.sl_perm_b.upload(perm_b.data(), perm_b.size(), c.stream);
   A.sl_col.upload(col.data(), col.size(), c.stream);
-  A.sl_val.alloc((size_t)total);
+  A.sl_val.alloc((size_t)(tot_a + tot_b));
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   A.sell = true;
 }
 
-void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag) {
+void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag, int64_t n_own_split) {
   A.tag = tag;
   A.nrows = (int32_t)h.nrows;
   A.ncols_own = (int32_t)h.ncols;
@@ -208,7 +240,7 @@ void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &
   const bool short_rows = A.mean_row < 64.0 && maxrow <= 8.0 * std::max(8.0, A.mean_row) && h.nrows >= 4096;
   const bool use_sell = c.spmv_mode == 2 || (c.spmv_mode == 0 && short_rows);
   if (use_sell) {
-    build_sell(c, A, h);
+    build_sell(c, A, h, n_own_split);
     A.col.release();
     A.val.release();
   } else {
@@ -249,22 +281,40 @@ void csr_set_values(Ctx &c, DevCsr &A, const HostCsr &h, const double *val, bool
 template <class Epi>
 static void spmv_launch(Ctx &c, const DevCsr &A, const double *x, const Epi &epi) {
   if (A.nrows == 0) return;
-  // multi-rank: fetch the ghost entries of x from their owners first
   const double *xg = nullptr;
   int nown = INT32_MAX;
   if (A.halo) {
-    halo_exchange(c, *A.halo, x);
     xg = A.halo->ghost.p;
     nown = A.ncols_own;
   }
   StageTimer kt(c, "spmv " + A.tag, 2);
   if (A.sell) {
     const int threads = 256;
-    const int grid = (int)(((int64_t)A.nslices * 32 + threads - 1) / threads);
-    spmv_sell_kernel<Epi><<<grid, threads, 0, c.stream>>>(A.nslices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p, A.sl_perm.p, x, xg, nown, epi);
-    FNP_LAUNCH_CHECK(c);
+    auto launch = [&](int nsl, const int32_t *ptr, const int32_t *perm, int64_t off) {
+      if (nsl <= 0) return;
+      const int grid = (int)(((int64_t)nsl * 32 + threads - 1) / threads);
+      spmv_sell_kernel<Epi><<<grid, threads, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, epi);
+      FNP_LAUNCH_CHECK(c);
+    };
+    if (A.halo && c.comm_stream) {
+      // interior rows run while the ghost entries travel: exchange on the communication
+      // stream, ordered by events (x is ready / the previous boundary pass has released
+      // the ghost buffer -> exchange; exchange done -> boundary rows)
+      FNP_CUDA(cudaEventRecord(c.ev_x, c.stream));
+      FNP_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_x, 0));
+      halo_exchange(c, *A.halo, x, c.comm_stream);
+      FNP_CUDA(cudaEventRecord(c.ev_halo, c.comm_stream));
+      launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0);
+      FNP_CUDA(cudaStreamWaitEvent(c.stream, c.ev_halo, 0));
+      launch(A.nslices_b, A.sl_ptr_b.p, A.sl_perm_b.p, A.sell_entries_a);
+    } else {
+      if (A.halo) halo_exchange(c, *A.halo, x, c.stream);
+      launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0);
+      launch(A.nslices_b, A.sl_ptr_b.p, A.sl_perm_b.p, A.sell_entries_a);
+    }
     return;
   }
+  if (A.halo) halo_exchange(c, *A.halo, x, c.stream);
   const int threads = 256;
   auto grid = [&](int lanes) { return (int)(((int64_t)A.nrows * lanes + threads - 1) / threads); };
   switch (A.lanes) {

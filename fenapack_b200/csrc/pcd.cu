@@ -162,6 +162,44 @@ void pc_apply(Ctx &c, const double *x_u, const double *x_p, double *y_u, double 
   u_solve(c, tu, y_u);
 }
 
+void Ctx::drop_graph() {
+  if (pc_graph) cudaGraphExecDestroy(pc_graph);
+  pc_graph = nullptr;
+  pc_graph_nodes = 0;
+}
+
+void pc_apply_vec(Ctx &c, const double *x, double *y) {
+  const int64_t n = c.n_u + c.n_p;
+  const bool graphable = c.use_graph && c.nranks == 1 && c.timers_on == 0 && c.stream != nullptr;  // the legacy default stream cannot be captured
+  if (!graphable) {
+    pc_apply(c, x, x + c.n_u, y, y + c.n_u);
+    return;
+  }
+  if (!c.pc_graph) {
+    c.g_in.ensure((size_t)n);
+    c.g_out.ensure((size_t)n);
+    const int64_t before = c.launches;
+    cudaGraph_t graph = nullptr;
+    FNP_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      pc_apply(c, c.g_in.p, c.g_in.p + c.n_u, c.g_out.p, c.g_out.p + c.n_u);
+    } catch (...) {
+      cudaStreamEndCapture(c.stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    FNP_CUDA(cudaStreamEndCapture(c.stream, &graph));
+    c.pc_graph_nodes = c.launches - before;
+    c.launches = before;                       // nothing ran yet; replays are counted below
+    FNP_CUDA(cudaGraphInstantiate(&c.pc_graph, graph, 0));
+    FNP_CUDA(cudaGraphDestroy(graph));
+  }
+  FNP_CUDA(cudaMemcpyAsync(c.g_in.p, x, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  FNP_CUDA(cudaGraphLaunch(c.pc_graph, c.stream));
+  FNP_CUDA(cudaMemcpyAsync(y, c.g_out.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  c.launches += c.pc_graph_nodes;
+}
+
 void system_matvec(Ctx &c, const double *x, double *y) {
   StageTimer t(c, "FENaPack: system MatMult");
   const double *xu = x, *xp = x + c.n_u;
@@ -183,6 +221,7 @@ static void build_amg(Ctx &c, int which, DevHierarchy &H, const AmgParams &p) {
 
 void setup_all(Ctx &c) {
   StageTimer t(c, "FENaPack: setup");
+  c.drop_graph();
   FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must be called before fnp_setup");
   // pressure side is always needed; the velocity side only when the context owns the
   // whole block-triangular apply (n_u == 0: Schur-complement-only mode, the python-PC path)
@@ -196,6 +235,7 @@ void setup_all(Ctx &c) {
   for (auto &b : c.p_w) b.ensure((size_t)c.n_p);
   for (auto &b : c.u_w) b.ensure((size_t)c.n_u);
   c.red_out.ensure(256);
+  c.red_partial.ensure((size_t)c.num_sms * 4 * 200);     // sized once: no allocation inside the hot path
   const int uidx = c.velocity_pc_index();
   // AMG hierarchies (Ap: once; velocity block: whenever its values changed)
   if (c.opt_ap.pc == PC_AMG && (c.dirty[FNP_MAT_AP] || !c.amg_ap.built)) build_amg(c, FNP_MAT_AP, c.amg_ap, c.opt_ap.amg);
