@@ -45,6 +45,7 @@ Ctx::~Ctx() {
   if (comm_stream) { cudaStreamSynchronize(comm_stream); cudaStreamDestroy(comm_stream); }
   if (ev_x) cudaEventDestroy(ev_x);
   if (ev_halo) cudaEventDestroy(ev_halo);
+  if (comm_halo) nccl().CommDestroy(comm_halo);
   if (comm) nccl().CommDestroy(comm);
   if (pinned) cudaFreeHost(pinned);
   for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -411,6 +412,9 @@ int fnp_create_dist(fnp_context **out, int device, const void *nccl_id, int rank
   ctx->c.rank = rank;
   ctx->c.nranks = nranks;
   if (nranks > 1) {
+    // a second communicator for the overlapped halo exchanges: NCCL operations of ONE
+    // communicator must not be in flight on two streams at once
+    if (nccl().CommSplit) FNP_NCCL(nccl().CommSplit(ctx->c.comm, 0, rank, &ctx->c.comm_halo, nullptr));
     FNP_CUDA(cudaStreamCreateWithFlags(&ctx->c.comm_stream, cudaStreamNonBlocking));
     FNP_CUDA(cudaEventCreateWithFlags(&ctx->c.ev_x, cudaEventDisableTiming));
     FNP_CUDA(cudaEventCreateWithFlags(&ctx->c.ev_halo, cudaEventDisableTiming));

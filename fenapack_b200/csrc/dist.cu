@@ -17,7 +17,7 @@ __global__ void pack_kernel(int32_t n, const int32_t *__restrict__ idx, const do
   if (i < n) buf[i] = x[idx[i]];
 }
 
-void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own, cudaStream_t stream) {
+void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own, cudaStream_t stream, ncclComm_t comm) {
   if (h.nsend > 0) {
     pack_kernel<<<(h.nsend + 255) / 256, 256, 0, stream>>>(h.nsend, h.send_idx.p, x_own, h.send_buf.p);
     c.launches++;
@@ -27,9 +27,9 @@ void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own, cudaStream_t stream
   FNP_NCCL(n.GroupStart());
   for (int q = 0; q < c.nranks; ++q) {
     if (h.send_count[q] > 0)
-      FNP_NCCL(n.Send(h.send_buf.p + h.send_off[q], (size_t)h.send_count[q], ncclDouble, q, c.comm, stream));
+      FNP_NCCL(n.Send(h.send_buf.p + h.send_off[q], (size_t)h.send_count[q], ncclDouble, q, comm, stream));
     if (h.recv_count[q] > 0)
-      FNP_NCCL(n.Recv(h.ghost.p + h.recv_off[q], (size_t)h.recv_count[q], ncclDouble, q, c.comm, stream));
+      FNP_NCCL(n.Recv(h.ghost.p + h.recv_off[q], (size_t)h.recv_count[q], ncclDouble, q, comm, stream));
   }
   FNP_NCCL(n.GroupEnd());
 }
@@ -171,7 +171,7 @@ std::shared_ptr<HaloPlan> build_halo(Ctx &c, HostCsr &h, const std::vector<int64
 std::vector<double> halo_exchange_host(Ctx &c, HaloPlan &plan, const std::vector<double> &x_own) {
   DevBuf<double> d(std::max<size_t>(x_own.size(), 1));
   if (!x_own.empty()) FNP_CUDA(cudaMemcpyAsync(d.p, x_own.data(), x_own.size() * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-  halo_exchange(c, plan, d.p, c.stream);
+  halo_exchange(c, plan, d.p, c.stream, c.comm);
   std::vector<double> g((size_t)plan.nghost);
   if (plan.nghost) FNP_CUDA(cudaMemcpyAsync(g.data(), plan.ghost.p, g.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   FNP_CUDA(cudaStreamSynchronize(c.stream));

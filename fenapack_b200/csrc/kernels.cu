@@ -296,25 +296,26 @@ static void spmv_launch(Ctx &c, const DevCsr &A, const double *x, const Epi &epi
       spmv_sell_kernel<Epi><<<grid, threads, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, epi);
       FNP_LAUNCH_CHECK(c);
     };
-    if (A.halo && c.comm_stream) {
+    // overlap pays only when the interior pass is long enough to hide an exchange (~30 us)
+    if (A.halo && c.comm_halo && A.nrows >= 100000) {
       // interior rows run while the ghost entries travel: exchange on the communication
       // stream, ordered by events (x is ready / the previous boundary pass has released
       // the ghost buffer -> exchange; exchange done -> boundary rows)
       FNP_CUDA(cudaEventRecord(c.ev_x, c.stream));
       FNP_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_x, 0));
-      halo_exchange(c, *A.halo, x, c.comm_stream);
+      halo_exchange(c, *A.halo, x, c.comm_stream, c.comm_halo);
       FNP_CUDA(cudaEventRecord(c.ev_halo, c.comm_stream));
       launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0);
       FNP_CUDA(cudaStreamWaitEvent(c.stream, c.ev_halo, 0));
       launch(A.nslices_b, A.sl_ptr_b.p, A.sl_perm_b.p, A.sell_entries_a);
     } else {
-      if (A.halo) halo_exchange(c, *A.halo, x, c.stream);
+      if (A.halo) halo_exchange(c, *A.halo, x, c.stream, c.comm);
       launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0);
       launch(A.nslices_b, A.sl_ptr_b.p, A.sl_perm_b.p, A.sell_entries_a);
     }
     return;
   }
-  if (A.halo) halo_exchange(c, *A.halo, x, c.stream);
+  if (A.halo) halo_exchange(c, *A.halo, x, c.stream, c.comm);
   const int threads = 256;
   auto grid = [&](int lanes) { return (int)(((int64_t)A.nrows * lanes + threads - 1) / threads); };
   switch (A.lanes) {

@@ -33,6 +33,7 @@ const NcclApi &nccl() {
   bind(h, g_api.GetUniqueId, "ncclGetUniqueId");
   bind(h, g_api.CommInitRank, "ncclCommInitRank");
   bind(h, g_api.CommDestroy, "ncclCommDestroy");
+  g_api.CommSplit = reinterpret_cast<decltype(g_api.CommSplit)>(dlsym(h, "ncclCommSplit"));   // optional (NCCL >= 2.18)
   bind(h, g_api.AllReduce, "ncclAllReduce");
   bind(h, g_api.AllGather, "ncclAllGather");
   bind(h, g_api.Send, "ncclSend");
