@@ -101,7 +101,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250"],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -270,7 +270,9 @@ def b200_arm(args):
     for _ in range(nwarm):
         its, rn, nap = ctx.solve_device(bu_p, bp_p, xu_p, xp_p)
     # ---- timed region: K solves, CUDA events on the library's stream ----------
-    with (ClockSampler(local) if not args.no_clocks else NoClocks()) as clk:
+    # one sampler per job (rank 0's GPU): N copies of nvidia-smi polling NVML perturb the
+    # launch-bound parts of a multi-rank run
+    with (ClockSampler(local) if (not args.no_clocks and rank == 0) else NoClocks()) as clk:
         barrier()
         l0 = ctx.kernel_launches()
         ctx.tic()
@@ -351,9 +353,15 @@ def b200_arm(args):
     ctx.set_option("fnp_timers", 0)
     peak, peak_src = hbm_peak()
     rpA, ciA, vaA = prob.A00
-    bytes_a00 = spmv_bytes(prob.n_u, prob.n_u, int(rpA[-1]))      # local rows; ghosts are a few planes
+    bs = ctx.block_size(capi.MAT_A00)
+    # algorithmic bytes of the operator AS STORED: in Kronecker mode (A00 = S (x) I_bs) the
+    # scalar operator is streamed once for bs vector rows; vectors keep their full length
+    bytes_a00 = 12.0 * int(rpA[-1]) / bs + 4.0 * (prob.n_u / bs + 1) + 16.0 * prob.n_u
     roof = {"bound": "hbm", "kernel": "spmv_sell_kernel<Epi> on A00 (P2 velocity block: AMG level-0 smoother/residual + outer MatMult)",
-            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "bytes_per_launch": bytes_a00}
+            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "bytes_per_launch": bytes_a00,
+            "kronecker_block_size": bs,
+            "bytes_note": "12 B per STORED entry + row pointers + y written once + x read once; with "
+                          "kronecker_block_size 3 the stored operator is the scalar S of A00 = S (x) I_3"}
     if "spmv A00" in stage:
         avg_ms = stage["spmv A00"]["ms"] / stage["spmv A00"]["calls"]
         roof["avg_launch_ms"] = avg_ms

@@ -55,6 +55,7 @@ SIGNATURES = {
     "fnp_solve_monolithic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _c_int32_p,
                                        _c_double_p, _c_int32_p]),
     "fnp_get_residual_history": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "fnp_operator_block_size": (C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
     "fnp_amg_num_levels": (C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
     "fnp_amg_level_info": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_int64_p, _c_int64_p,
                                      _c_int64_p, _c_double_p]),
@@ -300,6 +301,11 @@ class Context:
         cinv = np.empty((nc, nc))
         _check(self._lib.fnp_amg_coarse_inverse(self._h, which, _ptr(cinv)))
         return levels, cinv
+
+    def block_size(self, which):
+        bs = C.c_int32()
+        _check(self._lib.fnp_operator_block_size(self._h, which, C.byref(bs)))
+        return bs.value
 
     def amg_vcycle(self, which, b):
         b = _f64(b)

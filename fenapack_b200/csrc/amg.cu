@@ -18,7 +18,7 @@ void cheb_jacobi(Ctx &c, const DevCsr &A, const double *b, double emin, double e
                  const double *add, double *out, double *w0, double *w1) {
   FNP_REQUIRE(A.has_dinv, FNP_ERR_STATE, "Chebyshev-Jacobi: operator has no Jacobi diagonal (fnp_setup missing)");
   FNP_REQUIRE(steps >= 1, FNP_ERR_ARG, "Chebyshev-Jacobi needs ksp_max_it >= 1");
-  const int64_t n = A.nrows;
+  const int64_t n = A.vec_rows();
   const double s = 2.0 / (emax + emin);
   const double alpha = 1.0 - s * emin;
   const double mu = 1.0 / alpha;
@@ -57,18 +57,22 @@ void cheb_jacobi(Ctx &c, const DevCsr &A, const double *b, double emin, double e
   }
 }
 
-static void upload_csr(Ctx &c, const HostCsr &h, DevCsr &d, const std::string &tag,
+std::shared_ptr<HaloPlan> expand_plan(Ctx &c, const HaloPlan &p, int bs);
+
+static void upload_csr(Ctx &c, const HostCsr &h, DevCsr &d, const std::string &tag, int bs,
                        std::shared_ptr<HaloPlan> halo = nullptr, int64_t n_own = -1) {
-  csr_upload_pattern(c, d, h, tag, (halo && c.overlap) ? n_own : -1);
+  csr_upload_pattern(c, d, h, tag, (halo && c.overlap) ? n_own : -1, bs);
   csr_set_values(c, d, h, h.val.data(), false);
   if (halo) {
-    d.halo = halo;
+    d.halo = bs > 1 ? expand_plan(c, *halo, bs) : halo;
     d.ncols_own = (int32_t)n_own;
     d.nghost = halo->nghost;
   }
 }
 
-void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0) {
+// `bs` > 1: the host hierarchy is the one of the scalar operator S; every level acts on
+// bs interleaved right-hand sides (A_l (x) I_bs, P_l (x) I_bs, ...).
+void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0, int bs) {
   const size_t L = H.host.levels.size();
   H.levels.clear();
   H.levels.resize(L);
@@ -77,26 +81,42 @@ void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0
     DevLevel &dl = H.levels[l];
     if (l == 0 && level0) {
       dl.Ap = level0;
-      FNP_REQUIRE(level0->has_dinv && level0->nrows == hl.A.nrows, FNP_ERR_STATE, "AMG level 0 operator mismatch");
+      FNP_REQUIRE(level0->has_dinv && level0->nrows == hl.A.nrows && level0->bs == bs, FNP_ERR_STATE,
+                  "AMG level 0 operator mismatch");
     } else {
       dl.Ap = &dl.A_own;
-      upload_csr(c, hl.A, dl.A_own, name + "/L" + std::to_string(l), hl.halo, hl.n_own);
-      dl.A_own.dinv.upload(hl.dinv.data(), hl.dinv.size(), c.stream);
+      upload_csr(c, hl.A, dl.A_own, name + "/L" + std::to_string(l), bs, hl.halo, hl.n_own);
+      std::vector<double> dinv((size_t)hl.dinv.size() * bs);
+      for (size_t i = 0; i < hl.dinv.size(); ++i)
+        for (int b = 0; b < bs; ++b) dinv[i * bs + b] = hl.dinv[i];
+      dl.A_own.dinv.upload(dinv.data(), dinv.size(), c.stream);
+      FNP_CUDA(cudaStreamSynchronize(c.stream));
       dl.A_own.has_dinv = true;
     }
     dl.rho = hl.rho;
     if (l + 1 < L) {
-      upload_csr(c, hl.P, dl.P, name + "/P" + std::to_string(l));
-      upload_csr(c, hl.R, dl.R, name + "/R" + std::to_string(l));
+      upload_csr(c, hl.P, dl.P, name + "/P" + std::to_string(l), bs);
+      upload_csr(c, hl.R, dl.R, name + "/R" + std::to_string(l), bs);
     }
-    const size_t n = (size_t)hl.A.nrows;
+    const size_t n = (size_t)hl.A.nrows * bs;
     dl.x.alloc(n); dl.b.alloc(n); dl.r.alloc(n); dl.w0.alloc(n); dl.w1.alloc(n);
   }
-  H.coarse_n = (int)H.host.levels.back().A.nrows;
-  H.coarse_cols = (int)H.host.coarse_cols;
-  H.coarse_maxloc = (int)H.host.coarse_maxloc;
+  // coarsest level: dense inverse, expanded to the interleaved components
+  const int64_t nc = H.host.levels.back().A.nrows, cols = H.host.coarse_cols;
+  H.coarse_n = (int)(nc * bs);
+  H.coarse_cols = (int)(cols * bs);
+  H.coarse_maxloc = (int)(H.host.coarse_maxloc * bs);
   if (c.nranks > 1) H.coarse_gather.alloc((size_t)(c.nranks + 1) * H.coarse_maxloc);
-  H.coarse_inv.upload(H.host.coarse_inv.data(), H.host.coarse_inv.size(), c.stream);
+  if (bs == 1) {
+    H.coarse_inv.upload(H.host.coarse_inv.data(), H.host.coarse_inv.size(), c.stream);
+  } else {
+    std::vector<double> inv((size_t)H.coarse_n * H.coarse_cols, 0.0);
+    for (int64_t i = 0; i < nc; ++i)
+      for (int64_t j = 0; j < cols; ++j)
+        for (int b = 0; b < bs; ++b)
+          inv[(size_t)(i * bs + b) * H.coarse_cols + j * bs + b] = H.host.coarse_inv[(size_t)i * cols + j];
+    H.coarse_inv.upload(inv.data(), inv.size(), c.stream);
+  }
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   H.built = true;
 }

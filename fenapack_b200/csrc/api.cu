@@ -12,6 +12,7 @@ namespace fnp {
 std::vector<int64_t> comm_ranges(Ctx &c, int64_t n_local);
 std::shared_ptr<HaloPlan> build_halo(Ctx &c, HostCsr &h, const std::vector<int64_t> &begins,
                                      std::vector<int64_t> *ghost_global_out);
+std::shared_ptr<HaloPlan> expand_plan(Ctx &c, const HaloPlan &p, int bs);
 
 static thread_local std::string g_last_error;
 void set_last_error(const std::string &m) { g_last_error = m; }
@@ -200,6 +201,8 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
     else if (v == "csr") c.spmv_mode = 1;
     else if (v == "sell") c.spmv_mode = 2;
     else throw Error(FNP_ERR_OPTION, "option fnp_spmv_kernel: auto | csr | sell (takes effect at fnp_set_pattern)");
+  } else if (name == "fnp_kronecker") {
+    c.kron = parse_int(name, v);
   } else if (name == "fnp_halo_overlap") {
     c.overlap = parse_int(name, v);
   } else if (name == "fnp_cuda_graph") {
@@ -222,6 +225,27 @@ static void op_shape(const Ctx &c, int which, int64_t &nrows, int64_t &ncols) {
     case FNP_MAT_A10: nrows = c.n_p; ncols = c.n_u_global; break;
     default: nrows = c.n_p; ncols = c.n_p_global; break;
   }
+}
+
+double comm_allreduce(Ctx &c, double v, bool max_op);
+
+// Is the (sorted) pattern that of S (x) I_bs with interleaved components?  Rows bs*i+comp
+// must have equal length and columns bs*j+comp for the same nodes j.
+static bool kron_pattern(const HostCsr &h, int bs, int64_t col_shift_ok) {
+  if (bs < 2 || h.nrows == 0 || h.nrows % bs != 0 || h.ncols % bs != 0 || !col_shift_ok) return false;
+  const int64_t nn = h.nrows / bs;
+  bool ok = true;
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+  for (int64_t i = 0; i < nn; ++i) {
+    const int32_t b0 = h.rowptr[bs * i], len = h.rowptr[bs * i + 1] - b0;
+    for (int comp = 0; comp < bs && ok; ++comp) {
+      const int32_t b = h.rowptr[bs * i + comp];
+      if (h.rowptr[bs * i + comp + 1] - b != len) { ok = false; break; }
+      for (int32_t k = 0; k < len; ++k)
+        if (h.col[b + k] % bs != comp || h.col[b + k] / bs != h.col[b0 + k] / bs) { ok = false; break; }
+    }
+  }
+  return ok;
 }
 
 static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t *colidx) {
@@ -262,19 +286,48 @@ static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t 
   }
   static const char *names[FNP_MAT_COUNT] = {"A00", "A01", "A10", "Ap", "Mp", "Kp", "P00"};
   DevCsr &d = c.dmat[which];
+  // Kronecker detection for the velocity blocks (Picard/Oseen: the same scalar operator
+  // for every component).  Every rank must take the same decision.
+  int bs = 1;
+  if (c.kron && (which == FNP_MAT_A00 || which == FNP_MAT_P00)) {
+    for (int cand : {3, 2}) {
+      const bool aligned = c.u_begin % cand == 0 && c.n_u % cand == 0 && c.n_u_global % cand == 0;
+      double ok = kron_pattern(h, cand, aligned) ? 1.0 : 0.0;
+      ok = -comm_allreduce(c, -ok, true);          // min over ranks
+      if (ok > 0.5) { bs = cand; break; }
+    }
+  }
+  c.kron_bs[which] = bs;
+  c.kron_rowptr[which].clear();
+  if (bs > 1) {
+    // keep the scalar pattern (component 0 rows, node columns); remember the user's row
+    // pointers to pull and verify the values on every refresh
+    c.kron_rowptr[which] = h.rowptr;
+    HostCsr hs;
+    hs.nrows = h.nrows / bs;
+    hs.ncols = h.ncols / bs;
+    hs.rowptr.resize(hs.nrows + 1);
+    hs.rowptr[0] = 0;
+    for (int64_t i = 0; i < hs.nrows; ++i) hs.rowptr[i + 1] = hs.rowptr[i] + (h.rowptr[bs * i + 1] - h.rowptr[bs * i]);
+    hs.col.resize(hs.rowptr[hs.nrows]);
+    for (int64_t i = 0; i < hs.nrows; ++i)
+      for (int32_t k = 0; k < hs.rowptr[i + 1] - hs.rowptr[i]; ++k) hs.col[hs.rowptr[i] + k] = h.col[h.rowptr[bs * i] + k] / bs;
+    h = std::move(hs);
+  }
   if (c.nranks == 1) {
-    csr_upload_pattern(c, d, h, names[which]);
+    csr_upload_pattern(c, d, h, names[which], -1, bs);
   } else {
     // multi-rank: the device copy uses local column numbering [owned | ghost]; the host
     // copy keeps the global ids (the AMG set-up starts from them)
     const bool u_cols = which == FNP_MAT_A00 || which == FNP_MAT_P00 || which == FNP_MAT_A10;
-    const std::vector<int64_t> &begins = u_cols ? c.u_begins : c.p_begins;
+    std::vector<int64_t> begins = u_cols ? c.u_begins : c.p_begins;
+    for (auto &b : begins) b /= bs;               // scalar (node) ownership in Kronecker mode
     HostCsr loc = h;
     std::shared_ptr<HaloPlan> plan = build_halo(c, loc, begins, nullptr);
     const int64_t n_own_cols = begins[c.rank + 1] - begins[c.rank];
-    csr_upload_pattern(c, d, loc, names[which], c.overlap ? n_own_cols : -1);
-    d.halo = plan;
-    d.ncols_own = (int32_t)(begins[c.rank + 1] - begins[c.rank]);
+    csr_upload_pattern(c, d, loc, names[which], c.overlap ? n_own_cols : -1, bs);
+    d.halo = (plan && bs > 1) ? expand_plan(c, *plan, bs) : plan;
+    d.ncols_own = (int32_t)n_own_cols;
     d.nghost = plan ? plan->nghost : 0;
     c.local_cols[which] = std::move(loc.col);
   }
@@ -289,15 +342,39 @@ static void set_values(Ctx &c, int which, const double *values) {
   FNP_REQUIRE(c.have_pattern[which], FNP_ERR_STATE, "fnp_set_values before fnp_set_pattern");
   FNP_REQUIRE(values != nullptr || c.dmat[which].nnz == 0, FNP_ERR_ARG, "null values");
   HostCsr &h = c.hmat[which];
-  const int64_t nnz = h.nnz();
+  const int bs = c.kron_bs[which];
+  const int64_t nnz_user = bs > 1 ? (int64_t)c.kron_rowptr[which].back() : h.nnz();
   const std::vector<int64_t> &perm = c.perm[which];
   const double *src = values;
-  std::vector<double> tmp;
+  std::vector<double> tmp, tmps;
   if (!perm.empty()) {
-    tmp.resize(nnz);
-    for (int64_t k = 0; k < nnz; ++k) tmp[k] = values[perm[k]];
+    tmp.resize(nnz_user);
+    for (int64_t k = 0; k < nnz_user; ++k) tmp[k] = values[perm[k]];
     src = tmp.data();
   }
+  if (bs > 1) {
+    // scalar values = component 0; the other components must carry the same numbers
+    const std::vector<int32_t> &rp = c.kron_rowptr[which];
+    tmps.resize(h.nnz());
+    bool ok = true;
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+    for (int64_t i = 0; i < h.nrows; ++i) {
+      const int32_t len = h.rowptr[i + 1] - h.rowptr[i];
+      for (int32_t k = 0; k < len; ++k) {
+        const double v = src[rp[bs * i] + k];
+        tmps[h.rowptr[i] + k] = v;
+        for (int comp = 1; comp < bs; ++comp) {
+          const double w = src[rp[bs * i + comp] + k];
+          if (std::fabs(w - v) > 1e-13 * (std::fabs(v) + std::fabs(w))) ok = false;
+        }
+      }
+    }
+    FNP_REQUIRE(ok, FNP_ERR_STATE, "the velocity block has the pattern of S (x) I but its values differ between "
+                                   "components (Newton coupling / component-wise BCs?): set option fnp_kronecker 0 "
+                                   "before fnp_set_pattern");
+    src = tmps.data();
+  }
+  const int64_t nnz = h.nnz();
   if (keeps_host_values(which)) {
     h.val.assign(src, src + nnz);
     src = h.val.data();
@@ -540,8 +617,8 @@ int fnp_spmv(fnp_context *ctx, int which, const double *x, double *y, int on_dev
   FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT && c.have_values[which], FNP_ERR_STATE, "operator has no values");
   const DevCsr &A = c.dmat[which];
   Staged s(c, on_device != 0);
-  const double *dx = s.in(x, A.ncols_own);
-  double *dy = s.out(y, A.nrows);
+  const double *dx = s.in(x, A.vec_cols());
+  double *dy = s.out(y, A.vec_rows());
   spmv_store(c, A, dx, dy);
   s.finish();
   FNP_API_END
@@ -696,6 +773,14 @@ static const HostCsr &hier_mat(DevHierarchy &H, int level, int kind) {
   return kind == 0 ? L.A : (kind == 1 ? L.P : L.R);
 }
 
+int fnp_operator_block_size(fnp_context *ctx, int which, int32_t *bs) {
+  FNP_API_BEGIN
+  CTX(ctx);
+  FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT && bs, FNP_ERR_ARG, "bad argument");
+  *bs = c.kron_bs[which];
+  FNP_API_END
+}
+
 int fnp_amg_num_levels(fnp_context *ctx, int which, int32_t *levels) {
   FNP_API_BEGIN
   CTX(ctx);
@@ -738,7 +823,7 @@ int fnp_amg_vcycle(fnp_context *ctx, int which, const double *b, double *x, int 
   FNP_API_BEGIN
   CTX(ctx);
   DevHierarchy &H = hier(c, which);
-  const int64_t n = H.host.levels[0].A.nrows;
+  const int64_t n = H.levels[0].A().vec_rows();
   Staged s(c, on_device != 0);
   const double *db = s.in(b, n);
   double *dx = s.out(x, n);

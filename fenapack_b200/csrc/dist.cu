@@ -167,6 +167,29 @@ std::shared_ptr<HaloPlan> build_halo(Ctx &c, HostCsr &h, const std::vector<int64
   return plan;
 }
 
+// Plan for bs interleaved components per (scalar) entry of `p`.
+std::shared_ptr<HaloPlan> expand_plan(Ctx &c, const HaloPlan &p, int bs) {
+  auto e = std::make_shared<HaloPlan>();
+  const int R = (int)p.send_count.size();
+  e->send_count.resize(R); e->send_off.resize(R); e->recv_count.resize(R); e->recv_off.resize(R);
+  for (int q = 0; q < R; ++q) {
+    e->send_count[q] = p.send_count[q] * bs; e->send_off[q] = p.send_off[q] * bs;
+    e->recv_count[q] = p.recv_count[q] * bs; e->recv_off[q] = p.recv_off[q] * bs;
+  }
+  e->nsend = p.nsend * bs;
+  e->nghost = p.nghost * bs;
+  std::vector<int32_t> idx((size_t)std::max(p.nsend, 1)), idx2((size_t)std::max(e->nsend, 1));
+  if (p.nsend) FNP_CUDA(cudaMemcpyAsync(idx.data(), p.send_idx.p, p.nsend * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  for (int32_t i = 0; i < p.nsend; ++i)
+    for (int b = 0; b < bs; ++b) idx2[(size_t)i * bs + b] = idx[i] * bs + b;
+  e->send_idx.upload(idx2.data(), idx2.size(), c.stream);
+  e->send_buf.alloc((size_t)std::max(e->nsend, 1));
+  e->ghost.alloc((size_t)std::max(e->nghost, 1));
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  return e;
+}
+
 // Exchange one host vector through a halo plan: returns the ghost values (set-up helper).
 std::vector<double> halo_exchange_host(Ctx &c, HaloPlan &plan, const std::vector<double> &x_own) {
   DevBuf<double> d(std::max<size_t>(x_own.size(), 1));

@@ -122,6 +122,9 @@ void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own, cudaStream_t stream
 
 // Device-resident CSR operator; columns index [x_own | x_ghost].
 struct DevCsr {
+  int bs = 1;                // Kronecker block size: the operator is S (x) I_bs, S stored (kernels.cu)
+  int64_t vec_rows() const { return (int64_t)nrows * bs; }   // length of y
+  int64_t vec_cols() const { return (int64_t)ncols_own * bs; }   // owned length of x
   int32_t nrows = 0;
   int32_t ncols_own = 0;     // columns [0, ncols_own) address the owned part of x
   int32_t nghost = 0;        // columns [ncols_own, ncols_own+nghost) address the ghost buffer
@@ -143,7 +146,7 @@ struct DevCsr {
   double mean_row = 0.0, max_row = 0.0;
   // algorithmic bytes of one y = A x  (SURVEY 8d): 12 nnz + 4 (rows+1) + 8 rows + 8 cols
   double spmv_bytes() const {
-    return 12.0 * nnz + 4.0 * (nrows + 1) + 8.0 * nrows + 8.0 * (ncols_own + nghost);
+    return 12.0 * nnz + 4.0 * (nrows + 1) + 8.0 * bs * nrows + 8.0 * bs * (ncols_own + nghost);
   }
 };
 
@@ -165,7 +168,7 @@ struct EpiCheb {             // out = add + c0 p0 + c1 p1 + c2 dinv (b - A p1)  
 // Upload one operator: picks the storage format from the row-length histogram
 // (SELL-32-sigma for short rows, CSR + sub-warp-per-row kernel for long rows).
 // `val` may be null (pattern only); csr_set_values refreshes the numbers later.
-void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag, int64_t n_own_split = -1);
+void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag, int64_t n_own_split = -1, int bs = 1);
 void csr_set_values(Ctx &c, DevCsr &A, const HostCsr &pattern, const double *val, bool want_dinv);
 void spmv_store(Ctx &c, const DevCsr &A, const double *x, double *y);
 void spmv_axpby(Ctx &c, const DevCsr &A, const double *x, double a, double b, const double *z, double *y);
@@ -246,7 +249,7 @@ struct DevHierarchy {
   bool built = false;
 };
 
-void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0);
+void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0, int bs);
 // x = Vcycle(b), zero initial guess; b and x are level-0 sized device vectors (may not alias)
 void amg_vcycle(Ctx &c, DevHierarchy &H, const double *b, double *x);
 
@@ -314,6 +317,9 @@ struct Ctx {
   HostCsr hmat[FNP_MAT_COUNT];          // sorted host copies (pattern always; values for AMG operators)
   std::vector<int64_t> perm[FNP_MAT_COUNT];   // user order -> sorted order (empty = identity)
   std::vector<int32_t> local_cols[FNP_MAT_COUNT];   // multi-rank: columns in local [owned | ghost] numbering
+  int kron = 1;                                     // option fnp_kronecker: detect S (x) I_bs velocity blocks
+  int kron_bs[FNP_MAT_COUNT] = {1, 1, 1, 1, 1, 1, 1};
+  std::vector<int32_t> kron_rowptr[FNP_MAT_COUNT];  // row pointers of the expanded (user) pattern, for value checks
   bool have_pattern[FNP_MAT_COUNT] = {};
   bool have_values[FNP_MAT_COUNT] = {};
   bool dirty[FNP_MAT_COUNT] = {};

@@ -46,11 +46,17 @@ __device__ __forceinline__ void epilogue(const EpiCheb &e, int r, double s) {
 // x is addressed as [owned entries | ghost buffer]: column c < nown reads the caller's
 // vector, c >= nown reads the halo buffer filled by the exchange (dist.cu).  Single-GPU
 // contexts pass nown = INT_MAX.
-__device__ __forceinline__ double gather_x(const double *__restrict__ x, const double *__restrict__ xg, int nown, int c) {
-  return c < nown ? __ldg(x + c) : __ldg(xg + (c - nown));
+// Kronecker mode (BS > 1): the stored matrix is the scalar operator S of a vector-valued
+// block S (x) I_BS with interleaved components (dof = BS*node + comp), the case of the
+// Picard/Oseen velocity block and of every level of its AMG hierarchy.  One thread row
+// then serves BS vector rows: the (col, val) stream -- 12 B per scalar entry -- is read
+// once for BS results, cutting the matrix traffic by BS.
+template <int BS>
+__device__ __forceinline__ const double *gather_ptr(const double *__restrict__ x, const double *__restrict__ xg, int nown, int c) {
+  return c < nown ? x + (int64_t)BS * c : xg + (int64_t)BS * (c - nown);
 }
 
-template <int LANES, class Epi>
+template <int LANES, int BS, class Epi>
 __global__ void __launch_bounds__(256)
 spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             const double *__restrict__ val, const double *__restrict__ x, const double *__restrict__ xg, int nown,
@@ -58,22 +64,36 @@ spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__rest
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = tid / LANES;
   const int lane = tid % LANES;
-  double s0 = 0.0, s1 = 0.0;
+  double s0[BS], s1[BS];
+#pragma unroll
+  for (int b = 0; b < BS; ++b) s0[b] = s1[b] = 0.0;
   if (row < nrows) {
     const int beg = rowptr[row], end = rowptr[row + 1];
     int k = beg + lane;
     for (; k + LANES < end; k += 2 * LANES) {
       const int c0 = __ldg(col + k), c1 = __ldg(col + k + LANES);
       const double v0 = __ldg(val + k), v1 = __ldg(val + k + LANES);
-      s0 += v0 * gather_x(x, xg, nown, c0);
-      s1 += v1 * gather_x(x, xg, nown, c1);
-    }
-    if (k < end) s0 += __ldg(val + k) * gather_x(x, xg, nown, __ldg(col + k));
-  }
-  double s = s0 + s1;
+      const double *p0 = gather_ptr<BS>(x, xg, nown, c0), *p1 = gather_ptr<BS>(x, xg, nown, c1);
 #pragma unroll
-  for (int off = LANES / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, LANES);
-  if (row < nrows && lane == 0) epilogue(epi, row, s);
+      for (int b = 0; b < BS; ++b) {
+        s0[b] += v0 * __ldg(p0 + b);
+        s1[b] += v1 * __ldg(p1 + b);
+      }
+    }
+    if (k < end) {
+      const double v0 = __ldg(val + k);
+      const double *p0 = gather_ptr<BS>(x, xg, nown, __ldg(col + k));
+#pragma unroll
+      for (int b = 0; b < BS; ++b) s0[b] += v0 * __ldg(p0 + b);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < BS; ++b) {
+    double s = s0[b] + s1[b];
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, LANES);
+    if (row < nrows && lane == 0) epilogue(epi, BS * row + b, s);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -97,7 +117,7 @@ spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__rest
 constexpr int SELL_C = 32;
 constexpr int SELL_SIGMA = 1024;
 
-template <class Epi>
+template <int BS, class Epi>
 __global__ void __launch_bounds__(256)
 spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t *__restrict__ col,
                  const double *__restrict__ val, const int32_t *__restrict__ perm, const double *__restrict__ x,
@@ -110,20 +130,52 @@ spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t 
   const int row = __ldg(perm + slice * SELL_C + lane);
   const int32_t *cp = col + base + lane;
   const double *vp = val + base + lane;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int k = 0;
-  for (; k + 4 <= len; k += 4) {
-    const int c0 = __ldcs(cp + (k + 0) * SELL_C), c1 = __ldcs(cp + (k + 1) * SELL_C);
-    const int c2 = __ldcs(cp + (k + 2) * SELL_C), c3 = __ldcs(cp + (k + 3) * SELL_C);
-    const double v0 = __ldcs(vp + (k + 0) * SELL_C), v1 = __ldcs(vp + (k + 1) * SELL_C);
-    const double v2 = __ldcs(vp + (k + 2) * SELL_C), v3 = __ldcs(vp + (k + 3) * SELL_C);
-    s0 += v0 * gather_x(x, xg, nown, c0);
-    s1 += v1 * gather_x(x, xg, nown, c1);
-    s2 += v2 * gather_x(x, xg, nown, c2);
-    s3 += v3 * gather_x(x, xg, nown, c3);
+  if (BS == 1) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= len; k += 4) {
+      const int c0 = __ldcs(cp + (k + 0) * SELL_C), c1 = __ldcs(cp + (k + 1) * SELL_C);
+      const int c2 = __ldcs(cp + (k + 2) * SELL_C), c3 = __ldcs(cp + (k + 3) * SELL_C);
+      const double v0 = __ldcs(vp + (k + 0) * SELL_C), v1 = __ldcs(vp + (k + 1) * SELL_C);
+      const double v2 = __ldcs(vp + (k + 2) * SELL_C), v3 = __ldcs(vp + (k + 3) * SELL_C);
+      s0 += v0 * __ldg(gather_ptr<1>(x, xg, nown, c0));
+      s1 += v1 * __ldg(gather_ptr<1>(x, xg, nown, c1));
+      s2 += v2 * __ldg(gather_ptr<1>(x, xg, nown, c2));
+      s3 += v3 * __ldg(gather_ptr<1>(x, xg, nown, c3));
+    }
+    for (; k < len; ++k) s0 += __ldcs(vp + k * SELL_C) * __ldg(gather_ptr<1>(x, xg, nown, __ldcs(cp + k * SELL_C)));
+    if (row >= 0) epilogue(epi, row, (s0 + s1) + (s2 + s3));
+  } else {
+    double s0[BS], s1[BS];
+#pragma unroll
+    for (int b = 0; b < BS; ++b) s0[b] = s1[b] = 0.0;
+    int k = 0;
+    for (; k + 4 <= len; k += 4) {
+      const int c0 = __ldcs(cp + (k + 0) * SELL_C), c1 = __ldcs(cp + (k + 1) * SELL_C);
+      const int c2 = __ldcs(cp + (k + 2) * SELL_C), c3 = __ldcs(cp + (k + 3) * SELL_C);
+      const double v0 = __ldcs(vp + (k + 0) * SELL_C), v1 = __ldcs(vp + (k + 1) * SELL_C);
+      const double v2 = __ldcs(vp + (k + 2) * SELL_C), v3 = __ldcs(vp + (k + 3) * SELL_C);
+      const double *p0 = gather_ptr<BS>(x, xg, nown, c0), *p1 = gather_ptr<BS>(x, xg, nown, c1);
+      const double *p2 = gather_ptr<BS>(x, xg, nown, c2), *p3 = gather_ptr<BS>(x, xg, nown, c3);
+#pragma unroll
+      for (int b = 0; b < BS; ++b) {
+        s0[b] += v0 * __ldg(p0 + b);
+        s1[b] += v1 * __ldg(p1 + b);
+        s0[b] += v2 * __ldg(p2 + b);
+        s1[b] += v3 * __ldg(p3 + b);
+      }
+    }
+    for (; k < len; ++k) {
+      const double v0 = __ldcs(vp + k * SELL_C);
+      const double *p0 = gather_ptr<BS>(x, xg, nown, __ldcs(cp + k * SELL_C));
+#pragma unroll
+      for (int b = 0; b < BS; ++b) s0[b] += v0 * __ldg(p0 + b);
+    }
+    if (row >= 0) {
+#pragma unroll
+      for (int b = 0; b < BS; ++b) epilogue(epi, BS * row + b, s0[b] + s1[b]);
+    }
   }
-  for (; k < len; ++k) s0 += __ldcs(vp + k * SELL_C) * gather_x(x, xg, nown, __ldcs(cp + k * SELL_C));
-  if (row >= 0) epilogue(epi, row, (s0 + s1) + (s2 + s3));
 }
 
 static int pick_lanes(double mean_row) {
@@ -220,8 +272,9 @@ static void build_sell(Ctx &c, DevCsr &A, const HostCsr &h, int64_t n_own_split)
   A.sell = true;
 }
 
-void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag, int64_t n_own_split) {
+void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag, int64_t n_own_split, int bs) {
   A.tag = tag;
+  A.bs = bs;
   A.nrows = (int32_t)h.nrows;
   A.ncols_own = (int32_t)h.ncols;
   A.nghost = 0;
@@ -264,13 +317,14 @@ void csr_set_values(Ctx &c, DevCsr &A, const HostCsr &h, const double *val, bool
     A.val.upload(val, (size_t)nnz, c.stream);
   }
   if (want_dinv) {
-    std::vector<double> dinv((size_t)h.nrows, 0.0);
+    const int bs = A.bs;
+    std::vector<double> dinv((size_t)h.nrows * bs, 0.0);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < h.nrows; ++i) {
       double d = 0.0;
       for (int32_t k = h.rowptr[i]; k < h.rowptr[i + 1]; ++k)
         if (h.col[k] == i) d = val[k];
-      dinv[i] = d != 0.0 ? 1.0 / d : 0.0;
+      for (int b = 0; b < bs; ++b) dinv[(size_t)i * bs + b] = d != 0.0 ? 1.0 / d : 0.0;
     }
     A.dinv.upload(dinv.data(), dinv.size(), c.stream);
     A.has_dinv = true;
@@ -278,9 +332,8 @@ void csr_set_values(Ctx &c, DevCsr &A, const HostCsr &h, const double *val, bool
   FNP_CUDA(cudaStreamSynchronize(c.stream));
 }
 
-template <class Epi>
-static void spmv_launch(Ctx &c, const DevCsr &A, const double *x, const Epi &epi) {
-  if (A.nrows == 0) return;
+template <int BS, class Epi>
+static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &epi) {
   const double *xg = nullptr;
   int nown = INT32_MAX;
   if (A.halo) {
@@ -288,16 +341,16 @@ static void spmv_launch(Ctx &c, const DevCsr &A, const double *x, const Epi &epi
     nown = A.ncols_own;
   }
   StageTimer kt(c, "spmv " + A.tag, 2);
+  const int threads = 256;
   if (A.sell) {
-    const int threads = 256;
     auto launch = [&](int nsl, const int32_t *ptr, const int32_t *perm, int64_t off) {
       if (nsl <= 0) return;
       const int grid = (int)(((int64_t)nsl * 32 + threads - 1) / threads);
-      spmv_sell_kernel<Epi><<<grid, threads, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, epi);
+      spmv_sell_kernel<BS, Epi><<<grid, threads, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, epi);
       FNP_LAUNCH_CHECK(c);
     };
     // overlap pays only when the interior pass is long enough to hide an exchange (~30 us)
-    if (A.halo && c.comm_halo && A.nrows >= 100000) {
+    if (A.halo && c.comm_halo && c.overlap && A.nrows >= 100000) {
       // interior rows run while the ghost entries travel: exchange on the communication
       // stream, ordered by events (x is ready / the previous boundary pass has released
       // the ghost buffer -> exchange; exchange done -> boundary rows)
@@ -316,16 +369,29 @@ static void spmv_launch(Ctx &c, const DevCsr &A, const double *x, const Epi &epi
     return;
   }
   if (A.halo) halo_exchange(c, *A.halo, x, c.stream, c.comm);
-  const int threads = 256;
   auto grid = [&](int lanes) { return (int)(((int64_t)A.nrows * lanes + threads - 1) / threads); };
+#define FNP_VEC(L) \
+  spmv_kernel<L, BS, Epi><<<grid(L), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi)
   switch (A.lanes) {
-    case 2: spmv_kernel<2, Epi><<<grid(2), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); break;
-    case 4: spmv_kernel<4, Epi><<<grid(4), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); break;
-    case 8: spmv_kernel<8, Epi><<<grid(8), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); break;
-    case 16: spmv_kernel<16, Epi><<<grid(16), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); break;
-    default: spmv_kernel<32, Epi><<<grid(32), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); break;
+    case 2: FNP_VEC(2); break;
+    case 4: FNP_VEC(4); break;
+    case 8: FNP_VEC(8); break;
+    case 16: FNP_VEC(16); break;
+    default: FNP_VEC(32); break;
   }
+#undef FNP_VEC
   FNP_LAUNCH_CHECK(c);
+}
+
+template <class Epi>
+static void spmv_launch(Ctx &c, const DevCsr &A, const double *x, const Epi &epi) {
+  if (A.nrows == 0) return;
+  switch (A.bs) {
+    case 1: spmv_launch_bs<1, Epi>(c, A, x, epi); break;
+    case 2: spmv_launch_bs<2, Epi>(c, A, x, epi); break;
+    case 3: spmv_launch_bs<3, Epi>(c, A, x, epi); break;
+    default: throw Error(FNP_ERR_ARG, "unsupported block size");
+  }
 }
 
 void spmv_store(Ctx &c, const DevCsr &A, const double *x, double *y) { spmv_launch(c, A, x, EpiStore{y}); }

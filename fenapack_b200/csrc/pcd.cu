@@ -35,16 +35,16 @@ static void apply_inner_pc(Ctx &c, const InnerOpts &o, const DevCsr &A, DevHiera
   if (o.pc == PC_AMG) {
     amg_vcycle(c, *H, r, z);
   } else if (o.pc == PC_JACOBI) {
-    vec_pointwise_scale(c, A.nrows, 1.0, A.dinv.p, r, nullptr, z);
+    vec_pointwise_scale(c, A.vec_rows(), 1.0, A.dinv.p, r, nullptr, z);
   } else {
-    vec_copy(c, A.nrows, r, z);
+    vec_copy(c, A.vec_rows(), r, z);
   }
 }
 
 // Generic inner solve  x = KSP(A, PC)(b), zero initial guess.  work: 4 vectors.
 static void inner_solve(Ctx &c, const InnerOpts &o, const DevCsr &A, DevHierarchy *H, const double *b, double *x,
                         double *w0, double *w1, double *w2, double *w3) {
-  const int64_t n = A.nrows;
+  const int64_t n = A.vec_rows();
   switch (o.ksp) {
     case KSP_PREONLY:
       apply_inner_pc(c, o, A, H, b, x);
@@ -215,8 +215,11 @@ void system_matvec(Ctx &c, const double *x, double *y) {
 static void build_amg(Ctx &c, int which, DevHierarchy &H, const AmgParams &p) {
   H.params = p;
   const bool is_u = which == FNP_MAT_A00 || which == FNP_MAT_P00;
-  amg_build_host(c, c.hmat[which], is_u ? c.u_begins : c.p_begins, p, H.host);
-  amg_upload(c, H, which == FNP_MAT_AP ? "Ap" : "A00", &c.dmat[which]);
+  const int bs = c.kron_bs[which];
+  std::vector<int64_t> begins = is_u ? c.u_begins : c.p_begins;
+  for (auto &b : begins) b /= bs;              // Kronecker mode: the hierarchy is built on the scalar operator
+  amg_build_host(c, c.hmat[which], begins, p, H.host);
+  amg_upload(c, H, which == FNP_MAT_AP ? "Ap" : "A00", &c.dmat[which], bs);
 }
 
 void setup_all(Ctx &c) {

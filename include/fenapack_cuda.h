@@ -175,6 +175,11 @@ int fnp_get_residual_history(fnp_context *ctx, double *out, int32_t capacity);
 /* AMG hierarchy of `which` (FNP_MAT_AP or FNP_MAT_A00): number of levels, then
  * per level the CSR of A_l / P_l / R_l copied to caller buffers sized from
  * fnp_amg_level_info.  kind: 0 = A, 1 = P (level l+1 -> l), 2 = R. */
+/* Kronecker block size of a stored operator: bs > 1 means the library recognised
+ * A = S (x) I_bs (interleaved components; the Picard/Oseen velocity block) and stores /
+ * coarsens the scalar operator S only; the AMG introspection below then returns the
+ * levels of S.  Option fnp_kronecker 0 (before fnp_set_pattern) disables the detection. */
+int fnp_operator_block_size(fnp_context *ctx, int which, int32_t *bs);
 int fnp_amg_num_levels(fnp_context *ctx, int which, int32_t *levels);
 int fnp_amg_level_info(fnp_context *ctx, int which, int level, int kind, int64_t *nrows,
                        int64_t *ncols, int64_t *nnz, double *rho);

@@ -51,6 +51,11 @@ def make_context(prob, extra_options=None, device=0):
 def oracle_hierarchy_from_device(ctx, which, smooth_steps=2, eig_ratio=10.0):
     """The oracle V-cycle (oracle/amg.py) on the hierarchy the library built."""
     levels, cinv = ctx.amg_hierarchy(which)
+    bs = ctx.block_size(which)
+    if bs > 1:      # Kronecker mode: the library coarsens S of A = S (x) I_bs; expand for the oracle
+        eye = sp.identity(bs, format="csr")
+        levels = [{k: (sp.kron(v, eye, format="csr") if k != "rho" else v) for k, v in e.items()} for e in levels]
+        cinv = np.kron(cinv, np.eye(bs))
     H = oamg.Hierarchy(smooth_steps=smooth_steps, eig_ratio=eig_ratio)
     for e in levels:
         A = e["A"]
