@@ -231,6 +231,10 @@ def b200_arm(args):
     ctx.set_options(opts)
     if "FNP_OVERLAP" in os.environ:
         ctx.set_option("fnp_halo_overlap", os.environ["FNP_OVERLAP"])
+    if "FNP_P2P" in os.environ:
+        ctx.set_option("fnp_halo_p2p", os.environ["FNP_P2P"])
+    if "FNP_GRAPH" in os.environ:
+        ctx.set_option("fnp_cuda_graph", os.environ["FNP_GRAPH"])
     t0 = time.perf_counter()
     ctx.set_layout(prob.n_u, prob.n_p, prob.u_begin, prob.n_u_global, prob.p_begin, prob.n_p_global)
     for name, which in (("A00", capi.MAT_A00), ("A01", capi.MAT_A01), ("A10", capi.MAT_A10),

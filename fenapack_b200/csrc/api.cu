@@ -201,6 +201,8 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
     else if (v == "csr") c.spmv_mode = 1;
     else if (v == "sell") c.spmv_mode = 2;
     else throw Error(FNP_ERR_OPTION, "option fnp_spmv_kernel: auto | csr | sell (takes effect at fnp_set_pattern)");
+  } else if (name == "fnp_halo_p2p") {
+    c.p2p = parse_int(name, v);
   } else if (name == "fnp_kronecker") {
     c.kron = parse_int(name, v);
   } else if (name == "fnp_halo_overlap") {
@@ -325,7 +327,7 @@ static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t 
     HostCsr loc = h;
     std::shared_ptr<HaloPlan> plan = build_halo(c, loc, begins, nullptr);
     const int64_t n_own_cols = begins[c.rank + 1] - begins[c.rank];
-    csr_upload_pattern(c, d, loc, names[which], c.overlap ? n_own_cols : -1, bs);
+    csr_upload_pattern(c, d, loc, names[which], (c.overlap || c.p2p) ? n_own_cols : -1, bs);
     d.halo = (plan && bs > 1) ? expand_plan(c, *plan, bs) : plan;
     d.ncols_own = (int32_t)n_own_cols;
     d.nghost = plan ? plan->nghost : 0;
@@ -626,6 +628,15 @@ int fnp_spmv(fnp_context *ctx, int which, const double *x, double *y, int on_dev
 
 #define REQUIRE_SETUP() FNP_REQUIRE(c.is_setup, FNP_ERR_STATE, "fnp_setup has not been called")
 
+// a peer-memory flag wait that timed out (a neighbour rank died or fell out of step)
+static void check_p2p(Ctx &c) {
+  if (c.nranks == 1 || !c.p2p_err.p) return;
+  int e = 0;
+  FNP_CUDA(cudaMemcpyAsync(&e, c.p2p_err.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  FNP_REQUIRE(e == 0, FNP_ERR_NCCL, "peer-memory halo exchange timed out waiting for a neighbour rank");
+}
+
 int fnp_mp_solve(fnp_context *ctx, const double *b, double *x, int on_device) {
   FNP_API_BEGIN
   CTX(ctx);
@@ -686,6 +697,7 @@ int fnp_pc_apply(fnp_context *ctx, const double *x_u, const double *x_p, double 
   double *dyp = s.out(y_p, c.n_p);
   pc_apply(c, dxu, dxp, dyu, dyp);
   s.finish();
+  check_p2p(c);
   FNP_API_END
 }
 
@@ -715,6 +727,7 @@ int fnp_solve(fnp_context *ctx, const double *b_u, const double *b_p, double *x_
   if (iterations) *iterations = its;
   if (residual_norm) *residual_norm = rn;
   if (pc_applies) *pc_applies = nap;
+  check_p2p(c);
   FNP_API_END
 }
 

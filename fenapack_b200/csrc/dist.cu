@@ -4,12 +4,17 @@
 // exchanges are (i) the ghost entries of x before an SpMV (the MatMult VecScatter
 // of the reference) and (ii) small all-reduces for the Krylov scalars -- both NCCL
 // over NVLink, ordered on the context's stream.
+#include <dlfcn.h>
+
 #include <algorithm>
+#include <cstring>
 #include <numeric>
 
 #include "fnp_internal.cuh"
 
 namespace fnp {
+
+double comm_allreduce(Ctx &c, double v, bool max_op);
 
 __global__ void pack_kernel(int32_t n, const int32_t *__restrict__ idx, const double *__restrict__ x,
                             double *__restrict__ buf) {
@@ -17,7 +22,72 @@ __global__ void pack_kernel(int32_t n, const int32_t *__restrict__ idx, const do
   if (i < n) buf[i] = x[idx[i]];
 }
 
+// ---- peer-memory exchange ---------------------------------------------------------
+// send: every element goes straight into the neighbour's ghost slot (remote store over
+// NVLink); the last block to finish publishes the sequence number in the neighbours'
+// flag words.  __threadfence_system orders the data before the flag.
+__global__ void __launch_bounds__(256)
+p2p_send_kernel(int32_t nsend, const int32_t *__restrict__ idx, const double *__restrict__ x, int nranks,
+                const int *__restrict__ send_off, const int *__restrict__ send_cnt, double *const *__restrict__ peer_dst,
+                const long long *__restrict__ peer_stride, unsigned long long *const *__restrict__ peer_flag, int slot,
+                unsigned long long seq, unsigned int *counter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nsend) {
+    int q = 0;
+    while (q + 1 < nranks && i >= send_off[q] + send_cnt[q]) ++q;     // segments are ordered by peer
+    while (send_cnt[q] == 0 && q + 1 < nranks) ++q;
+    double *dst = peer_dst[q] + (long long)slot * peer_stride[q] + (i - send_off[q]);
+    *dst = x[idx[i]];
+  }
+  // block barrier, then ONE system-scope fence per block: the fence is cumulative over the
+  // stores the barrier made visible to thread 0 (a fence in every thread costs ~10x more)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      for (int q = 0; q < nranks; ++q)
+        if (send_cnt[q] > 0) *((volatile unsigned long long *)peer_flag[q]) = seq;
+    }
+  }
+}
+
+// wait: one thread per peer spins on the local flag word (bounded: ~4 s, then the error
+// flag is raised instead of hanging the GPU)
+__global__ void p2p_wait_kernel(int nranks, const int *__restrict__ recv_cnt, const unsigned long long *flags,
+                                unsigned long long seq, int *err) {
+  const int q = threadIdx.x;
+  if (q >= nranks || recv_cnt[q] == 0) return;
+  const long long t0 = clock64();
+  while (*((volatile const unsigned long long *)(flags + q)) < seq) {
+    if (clock64() - t0 > 8000000000ll) {
+      *err = 1;
+      return;
+    }
+  }
+}
+
+HaloPlan::~HaloPlan() {
+  for (void *p : peer_base)
+    if (p) cudaIpcCloseMemHandle(p);
+}
+
 void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own, cudaStream_t stream, ncclComm_t comm) {
+  if (h.p2p) {
+    const unsigned long long seq = ++h.seq;
+    const int slot = (int)(seq & 1ull);
+    if (h.nsend > 0) {
+      p2p_send_kernel<<<(h.nsend + 255) / 256, 256, 0, stream>>>(h.nsend, h.send_idx.p, x_own, c.nranks, h.d_send_off.p,
+                                                                  h.d_send_cnt.p, h.d_peer_dst.p, h.d_peer_stride.p,
+                                                                  h.d_peer_flag.p, slot, seq, h.d_counter.p);
+      c.launches++;
+      FNP_CUDA(cudaPeekAtLastError());
+    }
+    h.current_ghost = h.arena.p + (size_t)slot * h.nghost;
+    return;
+  }
   if (h.nsend > 0) {
     pack_kernel<<<(h.nsend + 255) / 256, 256, 0, stream>>>(h.nsend, h.send_idx.p, x_own, h.send_buf.p);
     c.launches++;
@@ -32,6 +102,113 @@ void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own, cudaStream_t stream
       FNP_NCCL(n.Recv(h.ghost.p + h.recv_off[q], (size_t)h.recv_count[q], ncclDouble, q, comm, stream));
   }
   FNP_NCCL(n.GroupEnd());
+  h.current_ghost = h.ghost.p;
+}
+
+void halo_wait(Ctx &c, HaloPlan &h, cudaStream_t stream) {
+  if (!h.p2p || h.nghost == 0) return;
+  p2p_wait_kernel<<<1, 32, 0, stream>>>(c.nranks, h.d_recv_cnt.p, reinterpret_cast<const unsigned long long *>(h.arena.p + 2 * (size_t)h.nghost),
+                                        h.seq, c.p2p_err.p);
+  c.launches++;
+  FNP_CUDA(cudaPeekAtLastError());
+}
+
+// cudaIpcGetMemHandle describes the BASE allocation a pointer lives in (cudaMalloc may
+// sub-allocate); the peers need the offset of our buffer inside it.
+static long long offset_in_allocation(const void *p) {
+  typedef int (*fn_t)(unsigned long long *, size_t *, unsigned long long);
+  static fn_t fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (h) fn = reinterpret_cast<fn_t>(dlsym(h, "cuMemGetAddressRange_v2"));
+  }
+  if (!fn) return -1;
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) return -1;
+  return (long long)((unsigned long long)(uintptr_t)p - base);
+}
+
+// Switch a plan to the peer-memory path.  Collective; every rank takes the same decision.
+void halo_enable_p2p(Ctx &c, HaloPlan &h) {
+  const int R = c.nranks, me = c.rank;
+  if (R == 1 || !c.p2p) return;
+  FNP_REQUIRE(R <= 32, FNP_ERR_ARG, "peer-memory halo supports up to 32 ranks");
+  // neighbour sets must be symmetric: the two-slot scheme relies on "I hear from q
+  // whenever I talk to q" to know that q has finished reading the slot I overwrite
+  double ok = 1.0;
+  for (int q = 0; q < R; ++q)
+    if ((h.send_count[q] > 0) != (h.recv_count[q] > 0)) ok = 0.0;
+  if (!c.p2p_err.p) {
+    c.p2p_err.alloc(1);
+    c.p2p_err.zero(c.stream);
+  }
+  // >= 2 MiB so that the arena is an allocation of its own (small cudaMallocs share a base
+  // block, and one IPC handle cannot be opened twice by the same peer)
+  h.arena.alloc(std::max<size_t>(2 * (size_t)h.nghost + (size_t)R, (size_t)262144));
+  h.arena.zero(c.stream);
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, h.arena.p) != cudaSuccess) { ok = 0.0; cudaGetLastError(); }
+  const long long my_offset = offset_in_allocation(h.arena.p);
+  if (my_offset < 0) ok = 0.0;
+  ok = -comm_allreduce(c, -ok, true);
+  if (ok < 0.5) { h.arena.release(); return; }
+  // all-gather: IPC handles (64 B), ghost counts, receive offsets
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  const size_t rec = 64 + sizeof(long long) * (2 + (size_t)R);
+  std::vector<char> sendrec(rec), all(rec * R);
+  std::memcpy(sendrec.data(), &mine, 64);
+  long long *meta = reinterpret_cast<long long *>(sendrec.data() + 64);
+  meta[0] = h.nghost;
+  meta[1] = my_offset;
+  for (int q = 0; q < R; ++q) meta[2 + q] = h.recv_off[q];
+  DevBuf<char> d(rec * (R + 1));
+  FNP_CUDA(cudaMemcpyAsync(d.p + rec * R, sendrec.data(), rec, cudaMemcpyHostToDevice, c.stream));
+  FNP_NCCL(nccl().AllGather(d.p + rec * R, d.p, rec, ncclChar, c.comm, c.stream));
+  FNP_CUDA(cudaMemcpyAsync(all.data(), d.p, rec * R, cudaMemcpyDeviceToHost, c.stream));
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  std::vector<double *> dst(R, nullptr);
+  std::vector<unsigned long long *> flag(R, nullptr);
+  std::vector<long long> stride(R, 0);
+  h.peer_base.assign(R, nullptr);
+  double opened = 1.0;
+  for (int q = 0; q < R; ++q) {
+    if (q == me || h.send_count[q] == 0) continue;
+    cudaIpcMemHandle_t hq;
+    std::memcpy(&hq, all.data() + rec * q, 64);
+    const long long *mq = reinterpret_cast<const long long *>(all.data() + rec * q + 64);
+    void *base = nullptr;
+    if (cudaIpcOpenMemHandle(&base, hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      opened = 0.0;
+      continue;
+    }
+    h.peer_base[q] = base;
+    double *arena_q = reinterpret_cast<double *>(static_cast<char *>(base) + mq[1]);
+    stride[q] = mq[0];
+    dst[q] = arena_q + mq[2 + me];                               // where q expects my entries
+    flag[q] = reinterpret_cast<unsigned long long *>(arena_q + 2 * mq[0]) + me;
+  }
+  opened = -comm_allreduce(c, -opened, true);
+  if (opened < 0.5) {
+    for (void *&p : h.peer_base) { if (p) cudaIpcCloseMemHandle(p); p = nullptr; }
+    h.arena.release();
+    return;
+  }
+  h.d_peer_dst.upload(dst.data(), R, c.stream);
+  h.d_peer_flag.upload(flag.data(), R, c.stream);
+  h.d_peer_stride.upload(stride.data(), R, c.stream);
+  h.d_send_off.upload(h.send_off.data(), R, c.stream);
+  h.d_send_cnt.upload(h.send_count.data(), R, c.stream);
+  h.d_recv_cnt.upload(h.recv_count.data(), R, c.stream);
+  h.d_counter.alloc(1);
+  h.d_counter.zero(c.stream);
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  // nobody may start sending before every rank has zeroed its flags and mapped its peers
+  comm_allreduce(c, 0.0, false);
+  h.p2p = true;
 }
 
 // ---- small host-level collectives (set-up time), staged through device memory ----
@@ -164,6 +341,7 @@ std::shared_ptr<HaloPlan> build_halo(Ctx &c, HostCsr &h, const std::vector<int64
   plan->ghost.alloc((size_t)std::max<int64_t>(ng, 1));
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   if (ghost_global_out) *ghost_global_out = ghosts;
+  halo_enable_p2p(c, *plan);
   return plan;
 }
 
@@ -187,6 +365,7 @@ std::shared_ptr<HaloPlan> expand_plan(Ctx &c, const HaloPlan &p, int bs) {
   e->send_buf.alloc((size_t)std::max(e->nsend, 1));
   e->ghost.alloc((size_t)std::max(e->nghost, 1));
   FNP_CUDA(cudaStreamSynchronize(c.stream));
+  if (p.p2p) halo_enable_p2p(c, *e);
   return e;
 }
 
@@ -195,8 +374,9 @@ std::vector<double> halo_exchange_host(Ctx &c, HaloPlan &plan, const std::vector
   DevBuf<double> d(std::max<size_t>(x_own.size(), 1));
   if (!x_own.empty()) FNP_CUDA(cudaMemcpyAsync(d.p, x_own.data(), x_own.size() * sizeof(double), cudaMemcpyHostToDevice, c.stream));
   halo_exchange(c, plan, d.p, c.stream, c.comm);
+  halo_wait(c, plan, c.stream);
   std::vector<double> g((size_t)plan.nghost);
-  if (plan.nghost) FNP_CUDA(cudaMemcpyAsync(g.data(), plan.ghost.p, g.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  if (plan.nghost) FNP_CUDA(cudaMemcpyAsync(g.data(), plan.current_ghost, g.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   return g;
 }

@@ -117,8 +117,26 @@ struct HaloPlan {
   int32_t nsend = 0, nghost = 0;
   DevBuf<int32_t> send_idx;
   DevBuf<double> send_buf, ghost;
+  // peer-memory path (one node, NVLink): the pack kernel stores straight into the ghost
+  // buffers of the neighbouring GPUs (cudaIpc mappings) and raises a flag there; the
+  // receiver spins on its local flags.  Two ghost slots alternate by sequence number.
+  bool p2p = false;
+  DevBuf<double> arena;                  // [2 * nghost doubles | nranks flags]
+  std::vector<void *> peer_base;         // opened IPC mappings (to close)
+  DevBuf<double *> d_peer_dst;           // per peer: my segment inside its slot 0
+  DevBuf<unsigned long long *> d_peer_flag;
+  DevBuf<long long> d_peer_stride;       // per peer: its nghost (slot stride)
+  DevBuf<int> d_send_off, d_send_cnt, d_recv_cnt;
+  DevBuf<unsigned int> d_counter;
+  unsigned long long seq = 0;
+  const double *current_ghost = nullptr; // what the SpMV kernels read after the last exchange
+  ~HaloPlan();
 };
+// posts the exchange of the ghost entries of x on `stream`; halo_wait makes them visible
+// (no-op for the NCCL path, flag wait for the peer-memory path)
 void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own, cudaStream_t stream, ncclComm_t comm);
+void halo_wait(Ctx &c, HaloPlan &h, cudaStream_t stream);
+void halo_enable_p2p(Ctx &c, HaloPlan &h);
 
 // Device-resident CSR operator; columns index [x_own | x_ghost].
 struct DevCsr {
@@ -344,9 +362,12 @@ struct Ctx {
 
   // CUDA graph of one block-triangular PC apply on fixed staging buffers (single-rank
   // contexts): ~500 short launches per apply collapse into one graph launch
+  int p2p = 0;                  // 1: peer-memory halo exchange (cudaIpc stores + flags).  Correct, but measured slower
+                                // than NCCL send/recv inside a CUDA graph (4.6 vs 3.7 ms per apply at N=2), so opt-in
+  DevBuf<int> p2p_err;          // set by a timed-out flag wait
   int overlap = 0;              // 1: split SELL operators into interior/boundary rows and overlap the halo exchange
                                 // on a second stream/communicator (measured SLOWER with NCCL send/recv: 5.8 vs 4.9 ms per apply)
-  int use_graph = 1;
+  int use_graph = 2;            // 0 off, 1 single-rank only, 2 also multi-rank (NCCL send/recv captured in the graph)
   cudaGraphExec_t pc_graph = nullptr;
   int64_t pc_graph_nodes = 0;
   DevBuf<double> g_in, g_out;

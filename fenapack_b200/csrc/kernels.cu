@@ -336,12 +336,14 @@ template <int BS, class Epi>
 static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &epi) {
   const double *xg = nullptr;
   int nown = INT32_MAX;
+  const int threads = 256;
   if (A.halo) {
-    xg = A.halo->ghost.p;
+    // post the exchange of the ghost entries of x (peer-memory stores or NCCL send/recv)
+    halo_exchange(c, *A.halo, x, c.stream, c.comm);
+    xg = A.halo->current_ghost;
     nown = A.ncols_own;
   }
   StageTimer kt(c, "spmv " + A.tag, 2);
-  const int threads = 256;
   if (A.sell) {
     auto launch = [&](int nsl, const int32_t *ptr, const int32_t *perm, int64_t off) {
       if (nsl <= 0) return;
@@ -349,26 +351,20 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
       spmv_sell_kernel<BS, Epi><<<grid, threads, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, epi);
       FNP_LAUNCH_CHECK(c);
     };
-    // overlap pays only when the interior pass is long enough to hide an exchange (~30 us)
-    if (A.halo && c.comm_halo && c.overlap && A.nrows >= 100000) {
-      // interior rows run while the ghost entries travel: exchange on the communication
-      // stream, ordered by events (x is ready / the previous boundary pass has released
-      // the ghost buffer -> exchange; exchange done -> boundary rows)
-      FNP_CUDA(cudaEventRecord(c.ev_x, c.stream));
-      FNP_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_x, 0));
-      halo_exchange(c, *A.halo, x, c.comm_stream, c.comm_halo);
-      FNP_CUDA(cudaEventRecord(c.ev_halo, c.comm_stream));
+    if (A.halo && A.nslices_b > 0) {
+      // split operator: the interior rows run while the ghost entries are in flight,
+      // the flag wait sits between the two passes (same stream, no extra events)
       launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0);
-      FNP_CUDA(cudaStreamWaitEvent(c.stream, c.ev_halo, 0));
+      halo_wait(c, *A.halo, c.stream);
       launch(A.nslices_b, A.sl_ptr_b.p, A.sl_perm_b.p, A.sell_entries_a);
     } else {
-      if (A.halo) halo_exchange(c, *A.halo, x, c.stream, c.comm);
+      if (A.halo) halo_wait(c, *A.halo, c.stream);
       launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0);
       launch(A.nslices_b, A.sl_ptr_b.p, A.sl_perm_b.p, A.sell_entries_a);
     }
     return;
   }
-  if (A.halo) halo_exchange(c, *A.halo, x, c.stream, c.comm);
+  if (A.halo) halo_wait(c, *A.halo, c.stream);
   auto grid = [&](int lanes) { return (int)(((int64_t)A.nrows * lanes + threads - 1) / threads); };
 #define FNP_VEC(L) \
   spmv_kernel<L, BS, Epi><<<grid(L), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi)

@@ -170,7 +170,9 @@ void Ctx::drop_graph() {
 
 void pc_apply_vec(Ctx &c, const double *x, double *y) {
   const int64_t n = c.n_u + c.n_p;
-  const bool graphable = c.use_graph && c.nranks == 1 && c.timers_on == 0 && c.stream != nullptr;  // the legacy default stream cannot be captured
+  // multi-rank: the apply contains NCCL send/recv (capturable since NCCL 2.9); opt-in with fnp_cuda_graph 2
+  const bool graphable = c.use_graph && (c.nranks == 1 || (c.use_graph >= 2 && !c.p2p)) && c.timers_on == 0 &&
+                         c.stream != nullptr;   // the legacy default stream cannot be captured
   if (!graphable) {
     pc_apply(c, x, x + c.n_u, y, y + c.n_u);
     return;

@@ -16,7 +16,7 @@ from fenapack_b200 import capi  # noqa: E402
 from oracle import amg as oamg  # noqa: E402
 from oracle import petsc_algos as pa  # noqa: E402
 from oracle import problems  # noqa: E402
-from util import ITERATIVE_OPTIONS, relerr  # noqa: E402
+from util import ITERATIVE_OPTIONS, oracle_hierarchy_like_library, relerr  # noqa: E402
 
 
 def split(n, world, align=1):
@@ -43,6 +43,8 @@ def main():
     opts["fieldsplit_p_pc_python_type"] = "fenapack.PCDPC_" + prob.variant
     opts["fieldsplit_p_PCD_Mp_ksp_chebyshev_eigenvalues"] = "%r, %r" % tuple(prob.cheb_bounds)
     ctx.set_options(opts)
+    if os.environ.get("FNP_P2P"):          # exercise the peer-memory halo path as well
+        ctx.set_option("fnp_halo_p2p", os.environ["FNP_P2P"])
     ctx.set_layout(u1 - u0, p1 - p0, u0, prob.n_u, p0, prob.n_p)
     P00 = prob.P00 if prob.P00 is not None else prob.A00
     mats = {capi.MAT_A00: (prob.A00, u0, u1), capi.MAT_A01: (prob.A01, u0, u1), capi.MAT_A10: (prob.A10, p0, p1),
@@ -63,7 +65,9 @@ def main():
         y = ctx.spmv(which, x[c0:c1], r1 - r0)
         assert relerr(y, (A @ x)[r0:r1]) <= 1e-12, ("spmv", which)
     # the preconditioner against the oracle with the same block-local hierarchy
-    Hu = oamg.build_hierarchy(P00, blocks=ub)
+    bs = ctx.block_size(capi.MAT_P00 if prob.P00 is not None else capi.MAT_A00)
+    assert bs == 3, "the Picard velocity block should be recognised as S (x) I_3"
+    Hu = oracle_hierarchy_like_library(P00, bs=bs, blocks=ub)
     Hp = oamg.build_hierarchy(prob.Ap, blocks=pb)
     pc = pa.PCDPreconditioner(prob, "iterative", amg_u=Hu, amg_p=Hp)
     b = rng.standard_normal(prob.n_p)
