@@ -89,54 +89,60 @@ def workload_name(args, dims, kind, variant, ndofs):
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU DURING the timed region.
+    In-process NVML (nvidia_ml_py) from a background thread: spawning nvidia-smi from a
+    process that holds a CUDA context, and its NVML polling, measurably perturb
+    launch-bound multi-rank runs."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index=0):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.proc = None
-        self.idx = gpu_index
+    def __init__(self, gpu_index=0, period=0.1):
+        self.idx, self.period = gpu_index, period
+        self.samples = []
+        self._stop = None
+        self._thr = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, pw, rs))
+                self._stop.wait(self.period)
+        except Exception as e:      # pragma: no cover
+            self.err = str(e)
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250"],
-                stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+        import threading
+        self._stop = threading.Event()
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
         return self
 
     def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        self._thr.join(timeout=5)
 
     def summary(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        try:
-            self.f.flush()
-            rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
-            sm = [float(r[1]) for r in rows if len(r) >= 9]
-            if sm:
-                out["samples"] = len(sm)
-                out["sm_mhz"] = float(np.median(sm))
-                out["sm_max_mhz"] = float(rows[0][2])
-                out["power_w_max"] = max(float(r[3]) for r in rows if len(r) >= 9)
-                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-                for k, nm in enumerate(names):
-                    if any(r[5 + k].strip().lower().startswith("active") for r in rows if len(r) >= 9):
-                        out["reasons"].append(nm)
-        except Exception as e:  # pragma: no cover
-            out["error"] = str(e)
-        finally:
-            try:
-                os.unlink(self.f.name)
-            except OSError:
-                pass
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(self.samples), "how": "NVML in-process"}
+        if self.samples:
+            out["sm_mhz"] = float(np.median([s[0] for s in self.samples]))
+            out["sm_max_mhz"] = float(getattr(self, "sm_max", 0))
+            out["power_w_max"] = max(s[1] for s in self.samples)
+            for name, bit in self.REASONS:
+                if any(s[2] & bit for s in self.samples):
+                    out["reasons"].append(name)
+        if self.err:
+            out["error"] = self.err
         return out
 
 

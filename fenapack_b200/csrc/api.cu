@@ -708,14 +708,12 @@ int fnp_solve(fnp_context *ctx, const double *b_u, const double *b_p, double *x_
   REQUIRE_SETUP();
   FNP_REQUIRE(b_u && b_p && x_u && x_p, FNP_ERR_ARG, "null vector");
   const int64_t n = c.n_u + c.n_p;
-  c.kr_b.ensure((size_t)n);
-  c.kr_x.ensure((size_t)n);
-  DevBuf<double> xs;   // solution in split layout [u;p]
-  xs.alloc((size_t)n);
+  // persistent staging of b and x in split layout [u;p] (no allocation per solve)
+  DevBuf<double> &xs = c.sol_x, &bs = c.sol_b;
+  xs.ensure((size_t)n);
+  bs.ensure((size_t)n);
   const cudaMemcpyKind in_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const cudaMemcpyKind out_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  DevBuf<double> bs;
-  bs.alloc((size_t)n);
   FNP_CUDA(cudaMemcpyAsync(bs.p, b_u, c.n_u * sizeof(double), in_kind, c.stream));
   FNP_CUDA(cudaMemcpyAsync(bs.p + c.n_u, b_p, c.n_p * sizeof(double), in_kind, c.stream));
   int32_t its = 0, nap = 0;
@@ -738,8 +736,8 @@ int fnp_solve_monolithic(fnp_context *ctx, const double *b, double *x, int on_de
   REQUIRE_SETUP();
   FNP_REQUIRE(c.have_is, FNP_ERR_STATE, "fnp_solve_monolithic needs fnp_set_index_sets");
   const int64_t n = c.n_u + c.n_p;
-  DevBuf<double> mono, bs, xs;
-  mono.alloc((size_t)n); bs.alloc((size_t)n); xs.alloc((size_t)n);
+  DevBuf<double> &mono = c.sol_m, &bs = c.sol_b, &xs = c.sol_x;
+  mono.ensure((size_t)n); bs.ensure((size_t)n); xs.ensure((size_t)n);
   const double *dmono = b;
   if (!on_device) {
     FNP_CUDA(cudaMemcpyAsync(mono.p, b, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));

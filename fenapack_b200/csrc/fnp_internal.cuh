@@ -376,6 +376,7 @@ struct Ctx {
   // Krylov basis
   std::vector<DevBuf<double>> V, Z;
   DevBuf<double> kr_w, kr_x, kr_b;
+  DevBuf<double> sol_x, sol_b, sol_m;   // staging of the user's b / x (split and monolithic layouts)
   std::vector<double> res_hist;
 
   // timers
