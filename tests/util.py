@@ -77,19 +77,6 @@ def relerr(a, b):
 
 
 def oracle_hierarchy_like_library(A, bs=1, blocks=None, **kw):
-    """The oracle's own hierarchy set-up arranged the way the library does it: in
-    Kronecker mode (bs > 1) the scalar operator S of A = S (x) I_bs is coarsened (node
-    blocks for a multi-rank partition) and every level is expanded back."""
-    A = sp.csr_matrix(A)
-    if bs == 1:
-        return oamg.build_hierarchy(A, blocks=blocks, **kw)
-    S = A[::bs, :][:, ::bs].tocsr()
-    Hs = oamg.build_hierarchy(S, blocks=None if blocks is None else [b // bs for b in blocks], **kw)
-    eye = sp.identity(bs, format="csr")
-    H = oamg.Hierarchy(smooth_steps=Hs.smooth_steps, eig_ratio=Hs.eig_ratio)
-    for l in Hs.levels:
-        H.levels.append(oamg.Level(A=sp.kron(l.A, eye, format="csr"), dinv=np.repeat(l.dinv, bs), rho=l.rho,
-                                   P=None if l.P is None else sp.kron(l.P, eye, format="csr"),
-                                   R=None if l.R is None else sp.kron(l.R, eye, format="csr")))
-    H.coarse_inv = np.kron(Hs.coarse_inv, np.eye(bs))
-    return H
+    """The oracle's own hierarchy set-up arranged the way the library does it (Kronecker
+    mode coarsens the scalar operator): oracle.amg.build_hierarchy_kron."""
+    return oamg.build_hierarchy_kron(A, bs=bs, blocks=blocks, **kw)
