@@ -94,12 +94,51 @@ void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0
       dl.A_own.has_dinv = true;
     }
     dl.rho = hl.rho;
-    if (l + 1 < L) {
+    if (l + 1 < L || H.host.tail) {
       upload_csr(c, hl.P, dl.P, name + "/P" + std::to_string(l), bs);
       upload_csr(c, hl.R, dl.R, name + "/R" + std::to_string(l), bs);
     }
     const size_t n = (size_t)hl.A.nrows * bs;
     dl.x.alloc(n); dl.b.alloc(n); dl.r.alloc(n); dl.w0.alloc(n); dl.w1.alloc(n);
+  }
+  if (H.host.tail) {
+    // replicated tail: a serial hierarchy on every rank, fed by one padded all-gather
+    const std::vector<int64_t> &tb = H.host.tail_begins;
+    const int R = c.nranks;
+    int64_t maxloc = 0;
+    for (int q = 0; q < R; ++q) maxloc = std::max(maxloc, tb[q + 1] - tb[q]);
+    H.tail_n = tb[R] * bs;
+    H.tail_nloc = (tb[c.rank + 1] - tb[c.rank]) * bs;
+    H.tail_off = tb[c.rank] * bs;
+    H.tail_maxloc = maxloc * bs;
+    std::vector<int64_t> map((size_t)H.tail_n);
+    for (int q = 0; q < R; ++q)
+      for (int64_t t = 0; t < (tb[q + 1] - tb[q]) * bs; ++t) map[(size_t)(tb[q] * bs + t)] = (int64_t)q * H.tail_maxloc + t;
+    H.tail_map.upload(map.data(), map.size(), c.stream);
+    H.tail_gather.alloc((size_t)(R + 1) * H.tail_maxloc);
+    H.tail_gather.zero(c.stream);
+    H.tail_b.alloc((size_t)H.tail_n);
+    H.tail_x.alloc((size_t)H.tail_n);
+    H.tail_bloc.alloc((size_t)std::max<int64_t>(H.tail_nloc, 1));
+    FNP_CUDA(cudaStreamSynchronize(c.stream));
+    H.tail.reset(new DevHierarchy());
+    H.tail->params = H.params;
+    H.tail->serial = true;
+    H.tail->host = *H.host.tail;
+    const int saved_rank = c.rank, saved_n = c.nranks;
+    c.rank = 0;
+    c.nranks = 1;
+    try {
+      amg_upload(c, *H.tail, name + "/T", nullptr, bs);
+    } catch (...) {
+      c.rank = saved_rank;
+      c.nranks = saved_n;
+      throw;
+    }
+    c.rank = saved_rank;
+    c.nranks = saved_n;
+    H.built = true;
+    return;
   }
   // coarsest level: dense inverse, expanded to the interleaved components
   const int64_t nc = H.host.levels.back().A.nrows, cols = H.host.coarse_cols;
@@ -121,10 +160,24 @@ void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0
   H.built = true;
 }
 
+static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, double *x);
+
+// coarse part replicated on every rank: all-gather the restricted residual, run the serial
+// tail V-cycle, keep the own slice of the correction (returned pointer)
+static const double *tail_solve(Ctx &c, DevHierarchy &H, const double *b_loc) {
+  double *slot = H.tail_gather.p + (size_t)c.nranks * H.tail_maxloc;
+  if (H.tail_nloc) FNP_CUDA(cudaMemcpyAsync(slot, b_loc, H.tail_nloc * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  FNP_NCCL(nccl().AllGather(slot, H.tail_gather.p, (size_t)H.tail_maxloc, ncclDouble, c.comm, c.stream));
+  vec_gather(c, H.tail_n, H.tail_map.p, H.tail_gather.p, H.tail_b.p);
+  vcycle_level(c, *H.tail, 0, H.tail_b.p, H.tail_x.p);
+  return H.tail_x.p + H.tail_off;
+}
+
 static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, double *x) {
   DevLevel &L = H.levels[l];
-  if (l + 1 == H.levels.size()) {
-    if (c.nranks == 1) {
+  const bool last = l + 1 == H.levels.size();
+  if (last && !H.tail) {
+    if (c.nranks == 1 || H.serial) {
       dense_gemv(c, H.coarse_n, H.coarse_cols, H.coarse_inv.p, b, x);
     } else {
       // padded all-gather of the coarse right-hand side, then this rank's rows of the inverse
@@ -138,15 +191,22 @@ static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, dou
   }
   const AmgParams &p = H.params;
   const double emax = L.rho, emin = L.rho / p.eig_ratio;
-  DevLevel &C = H.levels[l + 1];
   // pre-smoothing from the zero initial guess
   cheb_jacobi(c, L.A(), b, emin, emax, p.smooth_steps, 1.0, nullptr, x, L.w0.p, L.w1.p);
   // r = b - A x ; b_c = R r
   spmv_axpby(c, L.A(), x, -1.0, 1.0, b, L.r.p);
-  spmv_store(c, L.R, L.r.p, C.b.p);
-  vcycle_level(c, H, l + 1, C.b.p, C.x.p);
+  const double *xc;
+  if (last) {          // the next level lives in the replicated tail
+    spmv_store(c, L.R, L.r.p, H.tail_bloc.p);
+    xc = tail_solve(c, H, H.tail_bloc.p);
+  } else {
+    DevLevel &C = H.levels[l + 1];
+    spmv_store(c, L.R, L.r.p, C.b.p);
+    vcycle_level(c, H, l + 1, C.b.p, C.x.p);
+    xc = C.x.p;
+  }
   // x += P x_c
-  spmv_axpby(c, L.P, C.x.p, 1.0, 1.0, x, x);
+  spmv_axpby(c, L.P, xc, 1.0, 1.0, x, x);
   // post-smoothing on the correction equation: x += cheb(A, b - A x)
   spmv_axpby(c, L.A(), x, -1.0, 1.0, b, L.r.p);
   cheb_jacobi(c, L.A(), L.r.p, emin, emax, p.smooth_steps, 1.0, x, x, L.w0.p, L.w1.p);

@@ -470,9 +470,11 @@ static void extend_prolongator(Ctx &c, const HostCsr &P, int64_t coarse_begin, H
 // boundary, P and R are block diagonal over ranks); the Galerkin product couples
 // neighbouring ranks through the ghost rows of P.  With one rank this is the plain
 // serial algorithm.
-void amg_build_host(Ctx &c, const HostCsr &A0, std::vector<int64_t> begins, const AmgParams &p, HostHierarchy &H) {
+void amg_build_host(Ctx &c, const HostCsr &A0, std::vector<int64_t> begins, const AmgParams &p, HostHierarchy &H,
+                    int level0) {
   H.levels.clear();
   H.coarse_inv.clear();
+  H.tail.reset();
   const int me = c.rank, R = c.nranks;
   HostCsr Ag = A0;                 // current level, global column ids
   while (true) {
@@ -487,10 +489,10 @@ void amg_build_host(Ctx &c, const HostCsr &A0, std::vector<int64_t> begins, cons
     csr_diag_inv(A, lvl.dinv);
     lvl.rho = comm_allreduce(c, estimate_rho(A, lvl.dinv), true);
     const int64_t n_global = begins[R];
-    if (n_global <= p.coarse_size || (int)H.levels.size() >= p.max_levels) break;
+    if (n_global <= p.coarse_size || (int)H.levels.size() + level0 >= p.max_levels) break;
     std::vector<int32_t> sp, sc, agg;
     std::vector<double> sv;
-    strength(A, p.theta * std::pow(0.5, (double)(H.levels.size() - 1)), sp, sc, sv);
+    strength(A, p.theta * std::pow(0.5, (double)(H.levels.size() - 1 + level0)), sp, sc, sv);
     const int64_t nagg = aggregate_greedy(A.nrows, sp, sc, sv, agg);
     std::vector<int64_t> cbegins = comm_ranges(c, nagg);
     if (cbegins[R] == 0 || cbegins[R] >= n_global) break;
@@ -551,6 +553,49 @@ void amg_build_host(Ctx &c, const HostCsr &A0, std::vector<int64_t> begins, cons
     Ag.col = std::move(gcol);
     Ag.ncols = cbegins[R];
     begins = cbegins;
+    if (R > 1 && begins[R] <= p.replicate_size) {
+      // gather the level on every rank and continue serially (identical on all ranks)
+      const int64_t nloc = Ag.nrows, nnzloc = Ag.nnz();
+      const int64_t maxrows = (int64_t)comm_allreduce(c, (double)nloc, true);
+      const int64_t maxnnz = (int64_t)comm_allreduce(c, (double)nnzloc, true);
+      std::vector<double> len(nloc), cold(nnzloc);
+      for (int64_t i = 0; i < nloc; ++i) len[i] = (double)(Ag.rowptr[i + 1] - Ag.rowptr[i]);
+      for (int64_t k = 0; k < nnzloc; ++k) cold[k] = (double)Ag.col[k];
+      std::vector<double> all_len = comm_allgather_padded(c, len.data(), nloc, std::max<int64_t>(maxrows, 1));
+      std::vector<double> all_col = comm_allgather_padded(c, cold.data(), nnzloc, std::max<int64_t>(maxnnz, 1));
+      std::vector<double> all_val = comm_allgather_padded(c, Ag.val.data(), nnzloc, std::max<int64_t>(maxnnz, 1));
+      HostCsr Af;
+      Af.nrows = Af.ncols = begins[R];
+      Af.rowptr.assign(begins[R] + 1, 0);
+      for (int q = 0; q < R; ++q)
+        for (int64_t i = 0; i < begins[q + 1] - begins[q]; ++i)
+          Af.rowptr[begins[q] + i + 1] = (int32_t)all_len[(size_t)q * std::max<int64_t>(maxrows, 1) + i];
+      for (int64_t i = 0; i < begins[R]; ++i) Af.rowptr[i + 1] += Af.rowptr[i];
+      Af.col.resize(Af.rowptr[begins[R]]);
+      Af.val.resize(Af.rowptr[begins[R]]);
+      for (int q = 0; q < R; ++q) {
+        const int64_t o = Af.rowptr[begins[q]], cnt = Af.rowptr[begins[q + 1]] - o;
+        for (int64_t k = 0; k < cnt; ++k) {
+          Af.col[o + k] = (int32_t)all_col[(size_t)q * std::max<int64_t>(maxnnz, 1) + k];
+          Af.val[o + k] = all_val[(size_t)q * std::max<int64_t>(maxnnz, 1) + k];
+        }
+      }
+      H.tail = std::make_shared<HostHierarchy>();
+      H.tail_begins = begins;
+      const int saved_rank = c.rank, saved_n = c.nranks;
+      c.rank = 0;
+      c.nranks = 1;                       // the helpers below short-circuit every collective
+      try {
+        amg_build_host(c, Af, {0, begins[R]}, p, *H.tail, level0 + (int)H.levels.size());
+      } catch (...) {
+        c.rank = saved_rank;
+        c.nranks = saved_n;
+        throw;
+      }
+      c.rank = saved_rank;
+      c.nranks = saved_n;
+      return;
+    }
   }
   // coarsest level: every rank inverts the (small) global matrix and keeps its own rows,
   // columns laid out as the padded all-gather of the right-hand side delivers them

@@ -229,6 +229,7 @@ struct AmgParams {
   double eig_ratio = 10.0;
   double omega_scale = 4.0 / 3.0;
   double p_trunc = 0.2;        // drop prolongator entries below p_trunc*max|row|, rescale to the row sum
+  int64_t replicate_size = 300000;   // multi-rank: levels with <= this many (global) rows are replicated on every rank
   double coarse_drop = 0.0;    // > 0: lump coarse entries below drop*sqrt(|a_ii||a_jj|) onto the diagonal
 };
 
@@ -245,10 +246,15 @@ struct HostHierarchy {
   std::vector<HostLevel> levels;
   std::vector<double> coarse_inv;   // dense row-major [n_own x coarse_cols]
   int64_t coarse_cols = 0, coarse_maxloc = 0;
+  // multi-rank: from the first level with <= replicate_size global rows on, the hierarchy is
+  // built and applied redundantly on every rank (one all-gather per V-cycle instead of a halo
+  // exchange per SpMV on levels whose kernels are far shorter than an exchange)
+  std::shared_ptr<HostHierarchy> tail;
+  std::vector<int64_t> tail_begins;  // ownership offsets of the first replicated level
 };
 
 void amg_build_host(Ctx &c, const HostCsr &A_global_cols, std::vector<int64_t> begins, const AmgParams &p,
-                    HostHierarchy &H);
+                    HostHierarchy &H, int level0 = 0);
 
 struct DevLevel {
   DevCsr A_own, P, R;
@@ -262,6 +268,11 @@ struct DevHierarchy {
   std::vector<DevLevel> levels;
   DevBuf<double> coarse_inv, coarse_gather;
   int coarse_n = 0, coarse_cols = 0, coarse_maxloc = 0;
+  bool serial = false;                 // replicated tail: applied without communication
+  std::unique_ptr<DevHierarchy> tail;
+  DevBuf<double> tail_gather, tail_b, tail_x, tail_bloc;
+  DevBuf<int64_t> tail_map;            // global dof -> position in the padded all-gather buffer
+  int64_t tail_n = 0, tail_nloc = 0, tail_off = 0, tail_maxloc = 0;
   AmgParams params;
   HostHierarchy host;     // kept for introspection / refresh
   bool built = false;
