@@ -205,12 +205,15 @@ def _block_of(begins, n):
 
 
 def build_hierarchy(A, theta=0.08, max_levels=12, coarse_size=400, smooth_steps=2,
-                    eig_ratio=10.0, omega_scale=4.0 / 3.0, coarse_drop=0.0, p_trunc=0.2, blocks=None):
+                    eig_ratio=10.0, omega_scale=4.0 / 3.0, coarse_drop=0.0, p_trunc=0.2, blocks=None,
+                    replicate_size=300000):
     """``blocks``: ownership offsets [0, n_1, ..., n] of a row partition.  With more
     than one block the aggregation and the prolongator smoothing are block local
     (no aggregate crosses a block boundary, P = T - omega D^-1 A_bd T with A_bd the
     block-diagonal part), exactly what the multi-rank library does; the Galerkin
-    product uses the full A.  One block = the plain serial algorithm."""
+    product uses the full A.  One block = the plain serial algorithm.  Levels with at most
+    ``replicate_size`` rows are coarsened serially again (the library gathers them on
+    every rank)."""
     H = Hierarchy(smooth_steps=smooth_steps, eig_ratio=eig_ratio)
     A = sp.csr_matrix(A)
     A.sort_indices()
@@ -264,6 +267,9 @@ def build_hierarchy(A, theta=0.08, max_levels=12, coarse_size=400, smooth_steps=
         lvl.P, lvl.R = P, R
         A = Ac
         begins = cbegins
+        if len(begins) > 2 and begins[-1] <= replicate_size:
+            # the library replicates small levels on every rank and continues serially
+            begins = [0, begins[-1]]
     H.coarse_inv = np.linalg.inv(H.levels[-1].A.toarray())
     return H
 

@@ -152,8 +152,10 @@ def test_block_local_hierarchy_reduces_to_the_serial_one_and_converges():
     H2 = amg.build_hierarchy(A, blocks=[0, 3 * (A.shape[0] // 6), A.shape[0]])
     # no aggregate crosses the block boundary: P is block diagonal
     P = H2.levels[0].P.tocoo()
-    b0, c0 = H2.begins[0][1], H2.begins[1][1]
+    b0 = H2.begins[0][1]
+    c0 = P.col[P.row < b0].max() + 1          # aggregates of block 0 are numbered first
     assert np.all((P.row < b0) == (P.col < c0))
+    assert H2.begins[1] == [0, H2.levels[1].A.shape[0]]     # small levels are coarsened serially again
     rng = np.random.default_rng(1)
     b = rng.standard_normal(A.shape[0])
     x = np.zeros_like(b)
