@@ -205,6 +205,8 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
     else throw Error(FNP_ERR_OPTION, "option fnp_spmv_kernel: auto | csr | sell (takes effect at fnp_set_pattern)");
   } else if (name == "fnp_halo_p2p") {
     c.p2p = parse_int(name, v);
+  } else if (name == "fnp_prune_zeros") {
+    c.prune = parse_int(name, v);
   } else if (name == "fnp_kronecker") {
     c.kron = parse_int(name, v);
   } else if (name == "fnp_halo_overlap") {
@@ -561,14 +563,76 @@ int fnp_set_layout(fnp_context *ctx, int64_t n_u_local, int64_t u_begin, int64_t
 int fnp_set_pattern(fnp_context *ctx, int which, const int32_t *rowptr, const int32_t *colidx) {
   FNP_API_BEGIN
   CTX(ctx);
-  set_pattern(c, which, rowptr, colidx);
+  FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must precede fnp_set_pattern");
+  FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT, FNP_ERR_ARG, "bad operator id");
+  FNP_REQUIRE(rowptr != nullptr, FNP_ERR_ARG, "null pattern");
+  c.user_rowptr[which].clear();
+  c.user_col[which].clear();
+  c.pattern_pending[which] = false;
+  if (c.prune && (which == FNP_MAT_A00 || which == FNP_MAT_P00)) {
+    // DOLFIN stores the velocity block with the dense per-cell coupling of all components,
+    // explicit zeros included: the pattern is finalised at the first
+    // fnp_set_values, when the stored zeros are known and can be dropped
+    int64_t nrows, ncols;
+    op_shape(c, which, nrows, ncols);
+    FNP_REQUIRE(rowptr[0] == 0, FNP_ERR_ARG, "rowptr[0] must be 0");
+    for (int64_t i = 0; i < nrows; ++i) FNP_REQUIRE(rowptr[i + 1] >= rowptr[i], FNP_ERR_ARG, "rowptr not monotone");
+    c.user_rowptr[which].assign(rowptr, rowptr + nrows + 1);
+    c.user_col[which].assign(colidx, colidx + rowptr[nrows]);
+    c.user_nnz[which] = rowptr[nrows];
+    c.prune_mask[which].clear();
+    c.pattern_pending[which] = true;
+    c.have_pattern[which] = true;
+    c.have_values[which] = false;
+  } else {
+    set_pattern(c, which, rowptr, colidx);
+  }
   FNP_API_END
 }
 
 int fnp_set_values(fnp_context *ctx, int which, const double *values) {
   FNP_API_BEGIN
   CTX(ctx);
-  set_values(c, which, values);
+  FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT, FNP_ERR_ARG, "bad operator id");
+  FNP_REQUIRE(c.have_pattern[which], FNP_ERR_STATE, "fnp_set_values before fnp_set_pattern");
+  const bool pruning = !c.user_rowptr[which].empty();
+  if (pruning) {
+    FNP_REQUIRE(values != nullptr, FNP_ERR_ARG, "null values");
+    const std::vector<int32_t> &rp = c.user_rowptr[which], &ci = c.user_col[which];
+    const int64_t nrows = (int64_t)rp.size() - 1, nnz = c.user_nnz[which];
+    const int64_t row0 = c.u_begin;                       // A00 / P00: square in the u numbering
+    std::vector<char> &keepmask = c.prune_mask[which];
+    // (re)build the pattern when it is still pending, or when an entry dropped earlier as a
+    // stored zero carries a value now (e.g. the convection term after a zero initial guess);
+    // the decision is collective because the pattern set-up is
+    double rebuild = c.pattern_pending[which] ? 1.0 : 0.0;
+    if (!c.pattern_pending[which])
+      for (int64_t k = 0; k < nnz; ++k)
+        if (!keepmask[k] && values[k] != 0.0) { rebuild = 1.0; break; }
+    rebuild = comm_allreduce(c, rebuild, true);
+    if (rebuild > 0.5) {
+      if (keepmask.size() != (size_t)nnz) keepmask.assign((size_t)nnz, 0);
+      std::vector<int32_t> prp(nrows + 1, 0), pci;
+      pci.reserve(nnz);
+      for (int64_t i = 0; i < nrows; ++i) {
+        for (int32_t k = rp[i]; k < rp[i + 1]; ++k) {
+          if (values[k] != 0.0 || ci[k] == row0 + i) keepmask[k] = 1;
+          if (keepmask[k]) pci.push_back(ci[k]);
+        }
+        prp[i + 1] = (int32_t)pci.size();
+      }
+      set_pattern(c, which, prp.data(), pci.data());
+      c.pattern_pending[which] = false;
+      c.is_setup = false;                                 // hierarchies / work space follow the new pattern
+    }
+    std::vector<double> packed;
+    packed.reserve(c.hmat[which].nnz() * (size_t)c.kron_bs[which]);
+    for (int64_t k = 0; k < nnz; ++k)
+      if (keepmask[k]) packed.push_back(values[k]);
+    set_values(c, which, packed.data());
+  } else {
+    set_values(c, which, values);
+  }
   FNP_API_END
 }
 

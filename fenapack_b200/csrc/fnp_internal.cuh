@@ -229,7 +229,9 @@ struct AmgParams {
   double eig_ratio = 10.0;
   double omega_scale = 4.0 / 3.0;
   double p_trunc = 0.2;        // drop prolongator entries below p_trunc*max|row|, rescale to the row sum
-  int64_t replicate_size = 300000;   // multi-rank: levels with <= this many (global) rows are replicated on every rank
+  int64_t replicate_size = 0;        // multi-rank, > 0: levels with <= this many (global) rows are gathered and
+                                     // coarsened/applied redundantly on every rank.  Off by default: +6 % at N=2
+                                     // but slower (and 27 instead of 20 iterations) at N=8 with 300000
   double coarse_drop = 0.0;    // > 0: lump coarse entries below drop*sqrt(|a_ii||a_jj|) onto the diagonal
 };
 
@@ -347,6 +349,11 @@ struct Ctx {
   std::vector<int64_t> perm[FNP_MAT_COUNT];   // user order -> sorted order (empty = identity)
   std::vector<int32_t> local_cols[FNP_MAT_COUNT];   // multi-rank: columns in local [owned | ghost] numbering
   int kron = 1;                                     // option fnp_kronecker: detect S (x) I_bs velocity blocks
+  int prune = 1;                                    // option fnp_prune_zeros: drop stored zeros of A00/P00 at the first upload
+  bool pattern_pending[FNP_MAT_COUNT] = {};
+  std::vector<int32_t> user_rowptr[FNP_MAT_COUNT], user_col[FNP_MAT_COUNT];
+  std::vector<char> prune_mask[FNP_MAT_COUNT];      // per user entry: kept (1) or dropped as a stored zero (0)
+  int64_t user_nnz[FNP_MAT_COUNT] = {};
   int kron_bs[FNP_MAT_COUNT] = {1, 1, 1, 1, 1, 1, 1};
   std::vector<int32_t> kron_rowptr[FNP_MAT_COUNT];  // row pointers of the expanded (user) pattern, for value checks
   bool have_pattern[FNP_MAT_COUNT] = {};

@@ -206,7 +206,7 @@ def _block_of(begins, n):
 
 def build_hierarchy(A, theta=0.08, max_levels=12, coarse_size=400, smooth_steps=2,
                     eig_ratio=10.0, omega_scale=4.0 / 3.0, coarse_drop=0.0, p_trunc=0.2, blocks=None,
-                    replicate_size=300000):
+                    replicate_size=0):
     """``blocks``: ownership offsets [0, n_1, ..., n] of a row partition.  With more
     than one block the aggregation and the prolongator smoothing are block local
     (no aggregate crosses a block boundary, P = T - omega D^-1 A_bd T with A_bd the

@@ -45,6 +45,10 @@ def main():
     ctx.set_options(opts)
     if os.environ.get("FNP_P2P"):          # exercise the peer-memory halo path as well
         ctx.set_option("fnp_halo_p2p", os.environ["FNP_P2P"])
+    repl = int(os.environ.get("FNP_REPL", "0"))     # replicated coarse tail of the hierarchies
+    if repl:
+        ctx.set_option("fieldsplit_u_pc_amg_replicate_size", repl)
+        ctx.set_option("fieldsplit_p_PCD_Ap_pc_amg_replicate_size", repl)
     ctx.set_layout(u1 - u0, p1 - p0, u0, prob.n_u, p0, prob.n_p)
     P00 = prob.P00 if prob.P00 is not None else prob.A00
     mats = {capi.MAT_A00: (prob.A00, u0, u1), capi.MAT_A01: (prob.A01, u0, u1), capi.MAT_A10: (prob.A10, p0, p1),
@@ -67,8 +71,8 @@ def main():
     # the preconditioner against the oracle with the same block-local hierarchy
     bs = ctx.block_size(capi.MAT_P00 if prob.P00 is not None else capi.MAT_A00)
     assert bs == 3, "the Picard velocity block should be recognised as S (x) I_3"
-    Hu = oracle_hierarchy_like_library(P00, bs=bs, blocks=ub)
-    Hp = oamg.build_hierarchy(prob.Ap, blocks=pb)
+    Hu = oracle_hierarchy_like_library(P00, bs=bs, blocks=ub, replicate_size=repl)
+    Hp = oamg.build_hierarchy(prob.Ap, blocks=pb, replicate_size=repl)
     pc = pa.PCDPreconditioner(prob, "iterative", amg_u=Hu, amg_p=Hp)
     b = rng.standard_normal(prob.n_p)
     assert relerr(ctx.ap_solve(b[p0:p1]), pc.solve_Ap(b)[p0:p1]) <= 1e-9, "ap_solve"

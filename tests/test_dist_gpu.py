@@ -18,12 +18,15 @@ def _ngpus():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant,p2p", [("BRM1", "0"), ("BRM2", "0"), ("BRM1", "1")])
-def test_two_rank_parity(variant, p2p):
-    """p2p = "1": halo exchange through peer memory (cudaIpc) instead of NCCL send/recv."""
+@pytest.mark.parametrize("variant,p2p,repl", [("BRM1", "0", "0"), ("BRM2", "0", "0"), ("BRM1", "1", "0"),
+                                              ("BRM2", "0", "100000")])
+def test_two_rank_parity(variant, p2p, repl):
+    """p2p = "1": halo exchange through peer memory (cudaIpc) instead of NCCL send/recv;
+    repl > 0: coarse levels replicated on every rank (pc_amg_replicate_size)."""
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
     os.environ["FNP_P2P"] = p2p
+    os.environ["FNP_REPL"] = repl
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "dist_worker.py"), variant]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)

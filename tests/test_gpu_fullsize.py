@@ -1,0 +1,89 @@
+"""Full-size checks on the bench workload (3D cavity, 64^3 bricks, 6.7 M dofs) through
+size-independent properties -- the oracle's V-cycle is too slow to run here as a checker:
+SpMV against an independent host product, linearity of the preconditioner, true residual
+of the FGMRES solution, bit-reproducibility, Kronecker vs general storage."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N = 64
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import torch
+    import bench
+    import bench_inputs as bi
+    from fenapack_b200 import capi
+    prob = bi.OseenBoxProblem(N, N, N, kind="cavity", variant="BRM2", device="cuda:0")
+    torch.cuda.empty_cache()
+
+    def make(extra=None):
+        ctx = capi.Context(0)
+        opts = dict(bench.OPTIONS)
+        opts["fieldsplit_p_pc_python_type"] = "fenapack.PCDPC_BRM2"
+        opts.update(extra or {})
+        ctx.set_options(opts)
+        ctx.set_layout(prob.n_u, prob.n_p)
+        for name, which in (("A00", capi.MAT_A00), ("A01", capi.MAT_A01), ("A10", capi.MAT_A10),
+                            ("Ap", capi.MAT_AP), ("Mp", capi.MAT_MP), ("Kp", capi.MAT_KP)):
+            rp, ci, va = getattr(prob, name)
+            ctx.set_pattern(which, rp, ci)
+            ctx.set_values(which, va)
+        ctx.set_bc(prob.bc_idx, prob.bc_val)
+        ctx.setup()
+        return ctx
+    ctx = make()
+    yield prob, ctx, make, capi
+    ctx.close()
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def test_spmv_against_host_product(setup):
+    prob, ctx, _, capi = setup
+    rng = np.random.default_rng(0)
+    for name, which in (("A00", capi.MAT_A00), ("A01", capi.MAT_A01), ("A10", capi.MAT_A10), ("Ap", capi.MAT_AP)):
+        A = prob.scipy(name)
+        x = rng.standard_normal(A.shape[1])
+        assert relerr(ctx.spmv(which, x, A.shape[0]), A @ x) <= 1e-12, name
+    assert ctx.block_size(capi.MAT_A00) == 3
+
+
+def test_preconditioner_is_linear(setup):
+    prob, ctx, _, _ = setup
+    rng = np.random.default_rng(1)
+    xu, xp = rng.standard_normal(prob.n_u), rng.standard_normal(prob.n_p)
+    yu, yp = rng.standard_normal(prob.n_u), rng.standard_normal(prob.n_p)
+    a, b = 0.7, -1.3
+    mu, mp = ctx.pc_apply(a * xu + b * yu, a * xp + b * yp)
+    m1u, m1p = ctx.pc_apply(xu, xp)
+    m2u, m2p = ctx.pc_apply(yu, yp)
+    assert relerr(mu, a * m1u + b * m2u) <= 1e-10 and relerr(mp, a * m1p + b * m2p) <= 1e-10
+
+
+def test_solution_true_residual_and_reproducibility(setup):
+    prob, ctx, _, _ = setup
+    xu, xp, its, rn, nap = ctx.solve(prob.b_u, prob.b_p)
+    ru = prob.b_u - prob.scipy("A00") @ xu - prob.scipy("A01") @ xp
+    rp = prob.b_p - prob.scipy("A10") @ xu
+    bn = np.sqrt(prob.b_u @ prob.b_u + prob.b_p @ prob.b_p)
+    true_rel = np.sqrt(ru @ ru + rp @ rp) / bn
+    assert true_rel <= 1.05e-6 and abs(true_rel - rn / bn) <= 1e-8
+    assert 10 <= its <= 40 and nap == its
+    xu2, xp2, its2, _, _ = ctx.solve(prob.b_u, prob.b_p)
+    assert its2 == its and np.array_equal(xu, xu2) and np.array_equal(xp, xp2)      # atomic-free reductions
+
+
+def test_kronecker_and_general_storage_agree(setup):
+    prob, ctx, make, capi = setup
+    xu, xp, its, _, _ = ctx.solve(prob.b_u, prob.b_p)
+    cg = make({"fnp_kronecker": 0})
+    assert cg.block_size(capi.MAT_A00) == 1
+    gu, gp, its_g, _, _ = cg.solve(prob.b_u, prob.b_p)
+    cg.close()
+    assert abs(its - its_g) <= 2
+    assert relerr(np.concatenate([gu, gp]), np.concatenate([xu, xp])) <= 1e-4     # both solved to rtol 1e-6

@@ -326,3 +326,60 @@ def test_against_committed_golden_fixture(variant):
     _, _, its, _, _ = ctx.solve(prob.b_u, prob.b_p)
     assert abs(its - int(g[f"{variant}_iter_its"][0])) <= 1
     ctx.close()
+
+
+def _on_pattern(pattern, M):
+    """Values of M laid out on the (larger) stored pattern of `pattern`."""
+    import scipy.sparse as sp
+    z = pattern.copy()
+    z.data[:] = 0.0
+    coo = [sp.coo_matrix(z), sp.coo_matrix(M)]
+    out = sp.coo_matrix((np.concatenate([c.data for c in coo]), (np.concatenate([c.row for c in coo]),
+                                                                 np.concatenate([c.col for c in coo]))),
+                        shape=z.shape).tocsr()
+    out.sort_indices()
+    assert out.nnz == pattern.nnz
+    return out.data
+
+
+def test_stored_zeros_are_pruned_and_kronecker_detected():
+    """DOLFIN stores the Picard velocity block with the dense coupling of all components,
+    explicit zeros included.  The library drops the stored zeros at the first upload (and
+    then recognises S (x) I_d); a refresh that makes a dropped entry non-zero re-opens the
+    pattern (collectively) instead of failing."""
+    import scipy.sparse as sp
+    prob, space = problems.lid_driven_cavity(5, dim=3, variant="BRM2")
+    newton, _ = problems.lid_driven_cavity(5, dim=3, variant="BRM2", newton=True)
+    # dense-coupled pattern = the Newton pattern, values of the Picard block (zeros stored)
+    pat = newton.A00.copy()
+    pat.data[:] = 0.0
+    coo = [sp.coo_matrix(pat), sp.coo_matrix(prob.A00)]
+    dense = sp.coo_matrix((np.concatenate([c.data for c in coo]), (np.concatenate([c.row for c in coo]),
+                                                                   np.concatenate([c.col for c in coo]))),
+                          shape=pat.shape).tocsr()
+    dense.sort_indices()
+    assert dense.nnz > 2.5 * prob.A00.nnz and abs(dense - prob.A00).max() == 0.0
+    import copy
+    pd = copy.copy(prob)
+    pd.A00 = dense
+    pd.P00 = None
+    ctx = make_context(pd)
+    assert ctx.block_size(capi.MAT_A00) == 3
+    x = np.random.default_rng(0).standard_normal(prob.n_u)
+    assert relerr(ctx.spmv(capi.MAT_A00, x, prob.n_u), prob.A00 @ x) <= TOL_SPMV
+    # value-only refresh in the user's (un-pruned) layout
+    d2 = dense.copy()
+    d2.data = d2.data * 2.0
+    ctx.set_values(capi.MAT_A00, d2.data)
+    assert relerr(ctx.spmv(capi.MAT_A00, x, prob.n_u), 2.0 * (prob.A00 @ x)) <= TOL_SPMV
+    # a dropped entry that becomes non-zero (Newton coupling switched on) re-opens the pattern
+    ctx.set_values(capi.MAT_A00, _on_pattern(dense, newton.A00))
+    ctx.setup()
+    assert ctx.block_size(capi.MAT_A00) == 1
+    assert relerr(ctx.spmv(capi.MAT_A00, x, prob.n_u), newton.A00 @ x) <= TOL_SPMV
+    ctx.close()
+    # pruning off: the general path on the dense-coupled pattern gives the same product
+    cg = make_context(pd, {"fnp_prune_zeros": 0})
+    assert cg.block_size(capi.MAT_A00) == 1
+    assert relerr(cg.spmv(capi.MAT_A00, x, prob.n_u), prob.A00 @ x) <= TOL_SPMV
+    cg.close()

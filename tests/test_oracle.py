@@ -149,7 +149,7 @@ def test_block_local_hierarchy_reduces_to_the_serial_one_and_converges():
     H1 = amg.build_hierarchy(A)
     H1b = amg.build_hierarchy(A, blocks=[0, A.shape[0]])
     assert [l.A.nnz for l in H1.levels] == [l.A.nnz for l in H1b.levels]
-    H2 = amg.build_hierarchy(A, blocks=[0, 3 * (A.shape[0] // 6), A.shape[0]])
+    H2 = amg.build_hierarchy(A, blocks=[0, 3 * (A.shape[0] // 6), A.shape[0]], replicate_size=100000)
     # no aggregate crosses the block boundary: P is block diagonal
     P = H2.levels[0].P.tocoo()
     b0 = H2.begins[0][1]
