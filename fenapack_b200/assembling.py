@@ -34,28 +34,22 @@ class PCDForm(object):
     def __init__(self, form, const=False, phantom=False):
         assert isinstance(const, bool) and isinstance(phantom, bool)
         self._form = form
-        self._const = const
-        self._phantom = phantom
+        # public properties, as in the reference (assembling.py:222-224)
+        self.constant = const
+        self.phantom = phantom
+
+    def dolfin_form(self):
+        return self._form
 
     @property
     def ufl(self):
         return self._form
 
-    form = ufl
-
     def is_constant(self):
-        return self._const
-
-    def constant(self, value=True):
-        self._const = bool(value)
-        return self
+        return self.constant
 
     def is_phantom(self):
-        return self._phantom
-
-    def phantom(self, value=True):
-        self._phantom = bool(value)
-        return self
+        return self.phantom
 
 
 def _symmetric_dirichlet(A, dofs):
@@ -100,13 +94,17 @@ class PCDAssembler(object):
         return self._W
 
     def get_pcd_form(self, key):
-        form = self._forms[key]
-        if form.ufl is None:
+        """Return form wrapped in ``PCDForm`` (reference assembling.py:108-114)."""
+        form = self._forms.get(key)
+        if form is None:
             raise AttributeError("Form '%s' requested by PCD not available" % key)
         return form
 
     def get_dolfin_form(self, key):
-        return self.get_pcd_form(key).ufl
+        form = self.get_pcd_form(key).dolfin_form()
+        if form is None:
+            raise AttributeError("Form '%s' requested by PCD not available" % key)
+        return form
 
     def pcd_bcs(self):
         if not self._bcs_pcd:

@@ -19,6 +19,7 @@ _lib = None
 
 # operator ids (enum fnp_operator)
 MAT_A00, MAT_A01, MAT_A10, MAT_AP, MAT_MP, MAT_KP, MAT_P00 = range(7)
+MAT_RP = 100      # derived operator of the PCDR variants (introspection / spmv only)
 MAT_NAMES = {"A00": MAT_A00, "A01": MAT_A01, "A10": MAT_A10, "Ap": MAT_AP, "Mp": MAT_MP,
              "Kp": MAT_KP, "P00": MAT_P00}
 
@@ -43,6 +44,8 @@ SIGNATURES = {
     "fnp_set_pattern": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "fnp_set_values": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "fnp_set_bc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "fnp_set_mu_diag": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fnp_rp_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fnp_set_index_sets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fnp_setup": (C.c_int, [C.c_void_p]),
     "fnp_spmv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
@@ -195,6 +198,15 @@ class Context:
         idx = np.ascontiguousarray(idx, dtype=np.int32)
         values = _f64(values)
         _check(self._lib.fnp_set_bc(self._h, _ptr(idx), _ptr(values), idx.size))
+
+    def set_mu_diag(self, diag):
+        diag = _f64(diag)
+        if diag.size != self.n_u:
+            raise ValueError("Mu diagonal must have one entry per local velocity dof")
+        _check(self._lib.fnp_set_mu_diag(self._h, _ptr(diag)))
+
+    def rp_solve(self, b):
+        return self._solve1(self._lib.fnp_rp_solve, b, self.n_p)
 
     def set_index_sets(self, is_u, is_p):
         is_u = np.ascontiguousarray(is_u, dtype=np.int64)

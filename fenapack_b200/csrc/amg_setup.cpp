@@ -407,6 +407,9 @@ static void dense_inverse(const HostCsr &A, std::vector<double> &inv) {
   }
 }
 
+void host_spgemm(const HostCsr &A, const HostCsr &B, HostCsr &C) { spgemm(A, B, C); }
+void host_transpose(const HostCsr &A, HostCsr &T) { transpose(A, T); }
+
 // helpers from dist.cu
 std::vector<int64_t> comm_ranges(Ctx &c, int64_t n_local);
 double comm_allreduce(Ctx &c, double v, bool max_op);

@@ -37,6 +37,7 @@ Ctx::Ctx(int dev) : device(dev) {
   opt_u.ksp = KSP_RICHARDSON; opt_u.pc = PC_AMG; opt_u.max_it = 1;
   opt_ap.ksp = KSP_RICHARDSON; opt_ap.pc = PC_AMG; opt_ap.max_it = 2;
   opt_mp.ksp = KSP_CHEBYSHEV; opt_mp.pc = PC_JACOBI; opt_mp.max_it = 5; opt_mp.emin = 0.5; opt_mp.emax = 2.0;
+  opt_rp.ksp = KSP_RICHARDSON; opt_rp.pc = PC_AMG; opt_rp.max_it = 1;     // demo_unsteady-navier-stokes-pcdr.py:167-170
 }
 
 Ctx::~Ctx() {
@@ -177,12 +178,16 @@ static void set_inner_option(InnerOpts &o, const std::string &full, const std::s
 static void set_option(Ctx &c, const std::string &name, const std::string &v) {
   if (name.rfind("fnp_", 0) != 0) c.drop_graph();      // solver options are baked into the captured apply
   const std::string pu = "fieldsplit_u_", pap = "fieldsplit_p_PCD_Ap_", pmp = "fieldsplit_p_PCD_Mp_";
+  const std::string prp = "fieldsplit_p_PCD_Rp_";
+  if (starts_with(name, prp)) return set_inner_option(c.opt_rp, name, name.substr(prp.size()), v);
   if (starts_with(name, pap)) return set_inner_option(c.opt_ap, name, name.substr(pap.size()), v);
   if (starts_with(name, pmp)) return set_inner_option(c.opt_mp, name, name.substr(pmp.size()), v);
   if (starts_with(name, pu)) return set_inner_option(c.opt_u, name, name.substr(pu.size()), v);
   if (name == "fieldsplit_p_pc_python_type") {
     if (v == "fenapack.PCDPC_BRM1" || v == "BRM1") c.variant = 1;
     else if (v == "fenapack.PCDPC_BRM2" || v == "BRM2") c.variant = 2;
+    else if (v == "fenapack.PCDRPC_BRM1" || v == "PCDR_BRM1") c.variant = 3;
+    else if (v == "fenapack.PCDRPC_BRM2" || v == "PCDR_BRM2") c.variant = 4;
     else throw Error(FNP_ERR_OPTION, "option " + name + ": unsupported PCD class '" + v + "'");
   } else if (name == "ksp_type") {
     if (v == "gmres") c.flexible = false;
@@ -341,7 +346,9 @@ static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t 
   c.have_values[which] = false;
 }
 
-static bool keeps_host_values(int which) { return which == FNP_MAT_A00 || which == FNP_MAT_P00 || which == FNP_MAT_AP; }
+static bool keeps_host_values(int which) {
+  return which == FNP_MAT_A00 || which == FNP_MAT_P00 || which == FNP_MAT_AP || which == FNP_MAT_A01;   // A01: Rp of PCDR
+}
 
 static void set_values(Ctx &c, int which, const double *values) {
   FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT, FNP_ERR_ARG, "bad operator id");
@@ -650,6 +657,29 @@ int fnp_set_bc(fnp_context *ctx, const int32_t *idx_local, const double *values,
   FNP_API_END
 }
 
+int fnp_set_mu_diag(fnp_context *ctx, const double *diag_local) {
+  FNP_API_BEGIN
+  CTX(ctx);
+  FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must precede fnp_set_mu_diag");
+  FNP_REQUIRE(diag_local != nullptr || c.n_u == 0, FNP_ERR_ARG, "null diagonal");
+  c.mu_diag.assign(diag_local, diag_local + c.n_u);
+  c.mu_dirty = true;
+  FNP_API_END
+}
+
+int fnp_rp_solve(fnp_context *ctx, const double *b, double *x, int on_device) {
+  FNP_API_BEGIN
+  CTX(ctx);
+  FNP_REQUIRE(c.is_setup, FNP_ERR_STATE, "fnp_setup has not been called");
+  FNP_REQUIRE(c.variant >= 3, FNP_ERR_STATE, "Rp exists for the PCDR variants only");
+  Staged s(c, on_device != 0);
+  const double *db = s.in(b, c.n_p);
+  double *dx = s.out(x, c.n_p);
+  rp_solve(c, db, dx);
+  s.finish();
+  FNP_API_END
+}
+
 int fnp_set_index_sets(fnp_context *ctx, const int64_t *is_u_local, const int64_t *is_p_local) {
   FNP_API_BEGIN
   CTX(ctx);
@@ -682,8 +712,9 @@ int fnp_setup(fnp_context *ctx) {
 int fnp_spmv(fnp_context *ctx, int which, const double *x, double *y, int on_device) {
   FNP_API_BEGIN
   CTX(ctx);
-  FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT && c.have_values[which], FNP_ERR_STATE, "operator has no values");
-  const DevCsr &A = c.dmat[which];
+  FNP_REQUIRE(which == FNP_MAT_RP ? c.amg_rp.built || c.rp.nnz > 0 : (which >= 0 && which < FNP_MAT_COUNT && c.have_values[which]),
+              FNP_ERR_STATE, "operator has no values");
+  const DevCsr &A = which == FNP_MAT_RP ? c.rp : c.dmat[which];
   Staged s(c, on_device != 0);
   const double *dx = s.in(x, A.vec_cols());
   double *dy = s.out(y, A.vec_rows());
@@ -835,9 +866,9 @@ int fnp_get_residual_history(fnp_context *ctx, double *out, int32_t capacity) {
 
 // ---- introspection -------------------------------------------------------
 static DevHierarchy &hier(Ctx &c, int which) {
-  FNP_REQUIRE(which == FNP_MAT_AP || which == FNP_MAT_A00 || which == FNP_MAT_P00, FNP_ERR_ARG,
-              "AMG hierarchies exist for FNP_MAT_AP and FNP_MAT_A00 only");
-  DevHierarchy &H = which == FNP_MAT_AP ? c.amg_ap : c.amg_u;
+  FNP_REQUIRE(which == FNP_MAT_AP || which == FNP_MAT_A00 || which == FNP_MAT_P00 || which == FNP_MAT_RP, FNP_ERR_ARG,
+              "AMG hierarchies exist for FNP_MAT_AP, FNP_MAT_A00 and FNP_MAT_RP only");
+  DevHierarchy &H = which == FNP_MAT_AP ? c.amg_ap : (which == FNP_MAT_RP ? c.amg_rp : c.amg_u);
   FNP_REQUIRE(H.built, FNP_ERR_STATE, "AMG hierarchy not built");
   return H;
 }
@@ -853,8 +884,8 @@ static const HostCsr &hier_mat(DevHierarchy &H, int level, int kind) {
 int fnp_operator_block_size(fnp_context *ctx, int which, int32_t *bs) {
   FNP_API_BEGIN
   CTX(ctx);
-  FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT && bs, FNP_ERR_ARG, "bad argument");
-  *bs = c.kron_bs[which];
+  FNP_REQUIRE(((which >= 0 && which < FNP_MAT_COUNT) || which == FNP_MAT_RP) && bs, FNP_ERR_ARG, "bad argument");
+  *bs = which == FNP_MAT_RP ? 1 : c.kron_bs[which];
   FNP_API_END
 }
 

@@ -255,6 +255,8 @@ struct HostHierarchy {
   std::vector<int64_t> tail_begins;  // ownership offsets of the first replicated level
 };
 
+void host_spgemm(const HostCsr &A, const HostCsr &B, HostCsr &C);     // C = A B, rows sorted
+void host_transpose(const HostCsr &A, HostCsr &T);
 void amg_build_host(Ctx &c, const HostCsr &A_global_cols, std::vector<int64_t> begins, const AmgParams &p,
                     HostHierarchy &H, int level0 = 0);
 
@@ -340,7 +342,13 @@ struct Ctx {
   int restart = 150;
   double rtol = 1e-6, atol = 1e-50;
   int max_it = 10000;
-  InnerOpts opt_u, opt_ap, opt_mp;
+  InnerOpts opt_u, opt_ap, opt_mp, opt_rp;
+  // PCDR (reference preconditioners.py:173-298): Rp = Bt^T diag(Mu)^-1 Bt, built on the host from A01
+  std::vector<double> mu_diag;
+  bool mu_dirty = false;
+  HostCsr h_rp;
+  DevCsr rp;
+  DevHierarchy amg_rp;
   int spmv_mode = 0;            // 0 auto (by row-length histogram), 1 CSR vector kernel always, 2 SELL always
   int timers_on = 0;            // 0 off, 1 stage timers, 2 also one timer per SpMV launch
 
@@ -370,7 +378,7 @@ struct Ctx {
   DevHierarchy amg_u, amg_ap;
 
   // work space
-  DevBuf<double> p_w[6];      // pressure-sized work vectors
+  DevBuf<double> p_w[7];      // pressure-sized work vectors
   DevBuf<double> u_w[5];      // velocity-sized work vectors
   DevBuf<double> red_partial; // block partials of reductions
   DevBuf<double> red_out;     // small device results (h column, norms, CG scalars)
@@ -425,6 +433,7 @@ struct StageTimer {
 void setup_all(Ctx &c);
 void mp_solve(Ctx &c, const double *b, double out_scale, const double *add, double *x);
 void ap_solve(Ctx &c, const double *b, double *x);
+void rp_solve(Ctx &c, const double *b, double *x);
 void u_solve(Ctx &c, const double *b, double *x);
 void schur_apply(Ctx &c, const double *x_p, double *y_p);
 void pc_apply(Ctx &c, const double *x_u, const double *x_p, double *y_u, double *y_p);

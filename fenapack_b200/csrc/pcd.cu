@@ -113,6 +113,11 @@ void ap_solve(Ctx &c, const double *b, double *x) {
   inner_solve(c, c.opt_ap, c.dmat[FNP_MAT_AP], &c.amg_ap, b, x, c.p_w[1].p, c.p_w[2].p, c.p_w[3].p, c.p_w[4].p);
 }
 
+void rp_solve(Ctx &c, const double *b, double *x) {
+  StageTimer t(c, "FENaPack: PCD_Rp solve");
+  inner_solve(c, c.opt_rp, c.rp, &c.amg_rp, b, x, c.p_w[1].p, c.p_w[2].p, c.p_w[3].p, c.p_w[4].p);
+}
+
 void u_solve(Ctx &c, const double *b, double *x) {
   StageTimer t(c, "FENaPack: fieldsplit_u solve");
   inner_solve(c, c.opt_u, c.velocity_pc_matrix(), &c.amg_u, b, x, c.u_w[1].p, c.u_w[2].p, c.u_w[3].p, c.u_w[4].p);
@@ -122,8 +127,9 @@ void schur_apply(Ctx &c, const double *x, double *y) {
   const int64_t n = c.n_p;
   const DevCsr &Kp = c.dmat[FNP_MAT_KP];
   double *z = c.p_w[0].p;
-  if (c.variant == 1) {
-    StageTimer t(c, "FENaPack: PCDPC_BRM1 apply");
+  const bool pcdr = c.variant >= 3;            // PCDR: an extra -Rp^-1 x (preconditioners.py:251-262, 284-297)
+  if (c.variant == 1 || c.variant == 3) {
+    StageTimer t(c, pcdr ? "FENaPack: PCDRPC_BRM1 apply" : "FENaPack: PCDPC_BRM1 apply");
     // z = x ; z[bc] = g                        preconditioners.py:128-129
     vec_copy_bc(c, n, x, z, c.bc_idx.p, c.bc_val.p, c.nbc);
     // y = Ap^-1 z                              :130
@@ -133,7 +139,7 @@ void schur_apply(Ctx &c, const double *x, double *y) {
     // y = -Mp^-1 z                             :133-135
     mp_solve(c, z, -1.0, nullptr, y);
   } else {
-    StageTimer t(c, "FENaPack: PCDPC_BRM2 apply");
+    StageTimer t(c, pcdr ? "FENaPack: PCDRPC_BRM2 apply" : "FENaPack: PCDPC_BRM2 apply");
     double *z0 = c.p_w[5].p;
     // y = Mp^-1 x                              preconditioners.py:162
     mp_solve(c, x, 1.0, nullptr, y);
@@ -145,10 +151,17 @@ void schur_apply(Ctx &c, const double *x, double *y) {
     // y = -(y + z0)                            :167-169
     vec_axpby(c, n, -1.0, y, -1.0, z0, y);
   }
+  if (pcdr) {
+    // z = Rp^-1 x ; y = -(y_pcd + z)           :259-262 / :293-297 (the sign is already in y)
+    double *zr = c.p_w[6].p;
+    rp_solve(c, x, zr);
+    vec_axpy(c, n, -1.0, zr, y);
+  }
 }
 
 void pc_apply(Ctx &c, const double *x_u, const double *x_p, double *y_u, double *y_p) {
-  FNP_REQUIRE(c.n_u_global > 0, FNP_ERR_STATE, "this context holds the Schur-complement operators only (n_u = 0)");
+  FNP_REQUIRE(c.have_values[FNP_MAT_A00] && c.have_values[FNP_MAT_A01], FNP_ERR_STATE,
+              "this context holds the Schur-complement operators only (no velocity block)");
   StageTimer t(c, "FENaPack: PCD fieldsplit apply");
   // y_p = S^-1 x_p
   schur_apply(c, x_p, y_p);
@@ -232,11 +245,11 @@ void setup_all(Ctx &c) {
   // whole block-triangular apply (n_u == 0: Schur-complement-only mode, the python-PC path)
   for (int w : {(int)FNP_MAT_AP, (int)FNP_MAT_MP, (int)FNP_MAT_KP})
     FNP_REQUIRE(c.have_values[w], FNP_ERR_STATE, "fnp_setup: operator " + std::to_string(w) + " has no values");
-  const bool have_u = c.n_u_global > 0;
+  const bool have_u = c.have_values[FNP_MAT_A00];   // PCDR Schur-only contexts hold A01 but no velocity block
   if (have_u)
     for (int w : {(int)FNP_MAT_A00, (int)FNP_MAT_A01, (int)FNP_MAT_A10})
       FNP_REQUIRE(c.have_values[w], FNP_ERR_STATE, "fnp_setup: operator " + std::to_string(w) + " has no values");
-  FNP_REQUIRE(c.variant == 1 || c.variant == 2, FNP_ERR_STATE, "PCD variant not set");
+  FNP_REQUIRE(c.variant >= 1 && c.variant <= 4, FNP_ERR_STATE, "PCD variant not set");
   for (auto &b : c.p_w) b.ensure((size_t)c.n_p);
   for (auto &b : c.u_w) b.ensure((size_t)c.n_u);
   c.red_out.ensure(256);
@@ -245,6 +258,32 @@ void setup_all(Ctx &c) {
   // AMG hierarchies (Ap: once; velocity block: whenever its values changed)
   if (c.opt_ap.pc == PC_AMG && (c.dirty[FNP_MAT_AP] || !c.amg_ap.built)) build_amg(c, FNP_MAT_AP, c.amg_ap, c.opt_ap.amg);
   if (have_u && c.opt_u.pc == PC_AMG && (c.dirty[uidx] || !c.amg_u.built)) build_amg(c, uidx, c.amg_u, c.opt_u.amg);
+  if (c.variant >= 3) {
+    // PCDR: Rp = Bt^T diag(Mu)^-1 Bt with Bt = A01 (PCDInterface._build_approx_Ap,
+    // field_split_backend.py:142-166), rebuilt when A01 or Mu changed
+    FNP_REQUIRE(c.nranks == 1, FNP_ERR_STATE, "the PCDR variants are single-rank so far");
+    FNP_REQUIRE(c.have_values[FNP_MAT_A01] && (int64_t)c.mu_diag.size() == c.n_u, FNP_ERR_STATE,
+                "PCDR needs A01 (the discrete pressure gradient) and fnp_set_mu_diag");
+    if (c.dirty[FNP_MAT_A01] || c.mu_dirty || !c.amg_rp.built) {
+      const HostCsr &Bt = c.hmat[FNP_MAT_A01];
+      HostCsr S = Bt, B;                        // S = D^-1 Bt (rows scaled), B = Bt^T
+      for (int64_t i = 0; i < S.nrows; ++i) {
+        const double m = c.mu_diag[i];
+        const double f = m != 0.0 ? 1.0 / m : 0.0;
+        for (int32_t k = S.rowptr[i]; k < S.rowptr[i + 1]; ++k) S.val[k] *= f;
+      }
+      host_transpose(Bt, B);
+      host_spgemm(B, S, c.h_rp);
+      csr_upload_pattern(c, c.rp, c.h_rp, "Rp");
+      csr_set_values(c, c.rp, c.h_rp, c.h_rp.val.data(), true);
+      if (c.opt_rp.pc == PC_AMG) {
+        c.amg_rp.params = c.opt_rp.amg;
+        amg_build_host(c, c.h_rp, c.p_begins, c.opt_rp.amg, c.amg_rp.host);
+        amg_upload(c, c.amg_rp, "Rp", &c.rp, 1);
+      }
+      c.mu_dirty = false;
+    }
+  }
   for (int w = 0; w < FNP_MAT_COUNT; ++w) c.dirty[w] = false;
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   c.is_setup = true;

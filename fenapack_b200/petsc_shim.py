@@ -158,6 +158,13 @@ class Mat:
     def setOption(self, opt, flag):
         self._opts[opt] = flag
 
+    def getDiagonal(self, result=None):
+        d = self.csr.diagonal()
+        if result is None:
+            return Vec(d, self.comm)
+        result.array[:] = d
+        return result
+
     def getVecLeft(self):
         return Vec(np.zeros(self.csr.shape[0]), self.comm)
 

@@ -81,6 +81,9 @@ class BasePCDPC(object):
                     "and are not provided by libfenapack_cuda; use the iterative set-up "
                     "(richardson/cg + amg, chebyshev + jacobi)")
 
+    def _variant_name(self):
+        return "fenapack.PCDPC_" + self.variant
+
     def init_pcd(self, pcd_interface):
         """Initialize by PCDInterface instance (once; reference :64-68)."""
         if hasattr(self, "interface"):
@@ -96,7 +99,6 @@ class BasePCDPC(object):
     def _ensure_ctx(self, n_p):
         if self._ctx is None:
             self._ctx = capi.Context(self.interface.device if hasattr(self.interface, "device") else 0)
-            self._ctx.set_option("fieldsplit_p_pc_python_type", "fenapack.PCDPC_" + self.variant)
             self._ctx.set_options(self._device_opts)
             self._ctx.set_layout(0, n_p)
 
@@ -117,7 +119,7 @@ class BasePCDPC(object):
         n_p = self.mat_Mp.getSize()[0]
         self._ensure_ctx(n_p)
         ctx = self._ctx
-        ctx.set_option("fieldsplit_p_pc_python_type", "fenapack.PCDPC_" + self.variant)
+        ctx.set_option("fieldsplit_p_pc_python_type", self._variant_name())
         for which, mat, fresh in ((capi.MAT_MP, self.mat_Mp, Mp), (capi.MAT_AP, self.mat_Ap, Ap),
                                   (capi.MAT_KP, self.mat_Kp, Kp)):
             if fresh is None:
@@ -169,16 +171,69 @@ class PCDPC_BRM2(BasePCDPC):
     variant = "BRM2"
 
 
-class _NotProvided(BasePCDPC):
+class BasePCDRPC(BasePCDPC):
+    """Base python context of the pressure convection diffusion reaction (PCDR)
+    preconditioners (reference preconditioners.py:173-208): one more inner solver,
+    ``Rp = B diag(Mu)^-1 B^T`` with prefix ``<pc prefix>PCD_Rp_``, built by the library from
+    the discrete pressure gradient ``Bt`` and the diagonal of the velocity mass matrix."""
+
     def create(self, pc):
-        raise NotImplementedError(
-            type(self).__name__ + ": the PCDR variants (reference preconditioners.py:173-298) are outside "
-            "the hot path built so far (SURVEY.md 8f rank 1)")
+        super(BasePCDRPC, self).create(pc)
+        self._prefix_Rp = (pc.getOptionsPrefix() or "") + "PCD_Rp_"
+
+    def setFromOptions(self, pc):
+        opts = PETSc.Options(self._prefix_Rp)
+        for key in _INNER_KEYS:
+            val = opts.getString(key, None)
+            if val is not None:
+                self._device_opts["fieldsplit_p_PCD_Rp_" + key] = val
+        super(BasePCDRPC, self).setFromOptions(pc)
+
+    def _variant_name(self):
+        return "fenapack.PCDRPC_" + self.variant
+
+    def _ensure_ctx(self, n_p):
+        if self._ctx is None:
+            # Schur-only context that also holds Bt (u rows x p columns) for Rp
+            n_u = self.mat_Bt.getSize()[0]
+            self._ctx = capi.Context(self.interface.device if hasattr(self.interface, "device") else 0)
+            self._ctx.set_options(self._device_opts)
+            self._ctx.set_layout(n_u, n_p)
+
+    def setUp(self, pc):
+        itf = self.interface
+        # velocity mass matrix and discrete pressure gradient (reference :199-206)
+        Mu = itf.setup_mat_Mu(mat=getattr(self, "mat_Mu", None))
+        if Mu is not None:
+            self.mat_Mu = Mu
+            self.mat_Mu.setOptionsPrefix(self._pc_prefix + "PCD_Mu_")
+        Bt = itf.setup_mat_Bt(mat=getattr(self, "mat_Bt", None))
+        if Bt is not None:
+            self.mat_Bt = Bt
+            self.mat_Bt.setOptionsPrefix(self._pc_prefix + "PCD_Bt_")
+        owns = self._owns_ctx
+        self._owns_ctx = False                      # the base class must not call setup() yet
+        try:
+            super(BasePCDRPC, self).setUp(pc)
+        finally:
+            self._owns_ctx = owns
+        ctx = self._ctx
+        if Mu is not None:
+            ctx.set_mu_diag(self.mat_Mu.csr.diagonal() if hasattr(self.mat_Mu, "csr") else self.mat_Mu.getDiagonal().getArray())
+        if Bt is not None and owns:                 # PCDKSP uploads A01 itself in full-device mode
+            rp, ci, va = _mat_csr(self.mat_Bt)
+            if capi.MAT_A01 not in ctx._shapes:
+                ctx.set_pattern(capi.MAT_A01, rp, ci)
+            ctx.set_values(capi.MAT_A01, va)
+        if owns:
+            ctx.setup()
 
 
-class PCDRPC_BRM1(_NotProvided):
+class PCDRPC_BRM1(BasePCDRPC):
+    r"""``y = -Rp^{-1} x - Mp^{-1} (I + Kp Ap^{-1}) x`` -- reference preconditioners.py:212-262."""
     variant = "BRM1"
 
 
-class PCDRPC_BRM2(_NotProvided):
+class PCDRPC_BRM2(BasePCDRPC):
+    r"""``y = -Rp^{-1} x - (I + Ap^{-1} Kp) Mp^{-1} x`` -- reference preconditioners.py:266-298."""
     variant = "BRM2"

@@ -55,7 +55,9 @@ enum fnp_operator {
   FNP_MAT_KP = 5,  /* pressure convection (+reaction) matrix       field_split_backend.py:79-83 */
   FNP_MAT_P00 = 6, /* optional preconditioning velocity block (stabilised a_pc,
                       nonlinear_solvers.py:75-76); defaults to A00 */
-  FNP_MAT_COUNT = 7
+  FNP_MAT_COUNT = 7,
+  FNP_MAT_RP = 100 /* derived (PCDR): Rp = Bt^T diag(Mu)^-1 Bt, built by fnp_setup; valid for
+                      fnp_spmv and the AMG introspection calls only */
 };
 
 typedef struct fnp_context fnp_context;
@@ -88,9 +90,10 @@ int fnp_synchronize(fnp_context *ctx);
 /* PETSc options database names, without the user prefix, exactly as the
  * reference sets them (demo_navier-stokes-pcd.py:146-165):
  *   ksp_type gmres|fgmres, ksp_gmres_restart, ksp_rtol, ksp_atol, ksp_max_it
- *   fieldsplit_p_pc_python_type fenapack.PCDPC_BRM1|fenapack.PCDPC_BRM2
+ *   fieldsplit_p_pc_python_type fenapack.PCDPC_BRM1|fenapack.PCDPC_BRM2|fenapack.PCDRPC_BRM1|fenapack.PCDRPC_BRM2
  *   fieldsplit_u_ksp_type richardson, fieldsplit_u_ksp_max_it, fieldsplit_u_pc_type amg|jacobi
  *   fieldsplit_p_PCD_Ap_ksp_type richardson|cg, ..._ksp_max_it, ..._ksp_rtol, ..._pc_type amg|jacobi
+ *   fieldsplit_p_PCD_Rp_* like ..._Ap_* (PCDR only)
  *   fieldsplit_p_PCD_Mp_ksp_type chebyshev, ..._ksp_max_it, ..._ksp_chebyshev_eigenvalues "lo, hi",
  *   ..._pc_type jacobi
  *   <prefix>pc_amg_threshold, pc_amg_levels, pc_amg_coarse_size, pc_amg_smooth_steps,
@@ -121,6 +124,13 @@ int fnp_set_values(fnp_context *ctx, int which, const double *values);
  * SubfieldBC (SubfieldBC.h:48-53,92-160). */
 int fnp_set_bc(fnp_context *ctx, const int32_t *idx_local, const double *values, int32_t n);
 
+/* PCDR variants (PCDRPC_BRM1/2, preconditioners.py:173-298): diagonal of the velocity mass
+ * matrix Mu (Mat.getDiagonal of setup_mat_Mu, field_split_backend.py:100-105,147-148), local
+ * u numbering.  With it and A01 (= Bt, setup_mat_Bt :108-118) fnp_setup builds
+ * Rp = Bt^T diag(Mu)^-1 Bt (PCDInterface._build_approx_Ap :142-166) and its solver
+ * (options fieldsplit_p_PCD_Rp_*).  Single rank so far. */
+int fnp_set_mu_diag(fnp_context *ctx, const double *diag_local);
+
 /* Optional: positions of the local split dofs in the local monolithic vector
  * (dofmap_dofs_is, _field_split_utils.py:39-50).  Enables fnp_solve_monolithic. */
 int fnp_set_index_sets(fnp_context *ctx, const int64_t *is_u_local, const int64_t *is_p_local);
@@ -145,6 +155,7 @@ int fnp_spmv(fnp_context *ctx, int which, const double *x, double *y, int on_dev
 int fnp_mp_solve(fnp_context *ctx, const double *b, double *x, int on_device);
 int fnp_ap_solve(fnp_context *ctx, const double *b, double *x, int on_device);
 int fnp_u_solve(fnp_context *ctx, const double *b, double *x, int on_device);
+int fnp_rp_solve(fnp_context *ctx, const double *b, double *x, int on_device);   /* ksp_Rp.solve, preconditioners.py:259,293 */
 
 /* y_p = -S^-1 x_p : PCDPC_BRM1.apply / PCDPC_BRM2.apply
  * (preconditioners.py:98-135, 148-169) including apply_pcd_bcs

@@ -7,6 +7,8 @@ decides a detail.
   reference call site                                   restated here
   fenapack/preconditioners.py:124-135  (PCDPC_BRM1.apply)   brm1_apply
   fenapack/preconditioners.py:158-169  (PCDPC_BRM2.apply)   brm2_apply
+  fenapack/preconditioners.py:251-262, 284-297 (PCDRPC_*)   pcdr_brm1_apply, pcdr_brm2_apply
+  fenapack/field_split_backend.py:142-166 (_build_approx_Ap) build_rp
   fenapack/SubfieldBC.h:162-182        (VecSetValues INSERT) apply_bcs
   fenapack/field_split.py:52-57        (GMRES, right PC,    gmres_right / fgmres,
                                         fieldsplit SCHUR/UPPER) fieldsplit_upper_apply
@@ -129,6 +131,43 @@ def brm2_apply(x, solve_Ap, Kp, solve_Mp, bc_idx, bc_val):
     return -y                          # y.scale(-1.0)
 
 
+def build_rp(Bt, mu_diag):
+    """Approximate pressure Laplacian of the PCDR variants: Rp = B diag(Mu)^-1 B^T,
+    built as (D^-1/2 Bt)^T (D^-1/2 Bt) exactly as PCDInterface._build_approx_Ap does
+    (fenapack/field_split_backend.py:142-166)."""
+    d = np.sqrt(np.abs(1.0 / mu_diag))
+    S = sp.diags(d) @ sp.csr_matrix(Bt)
+    Rp = (S.T @ S).tocsr()
+    Rp.sort_indices()
+    return Rp
+
+
+def pcdr_brm1_apply(x, solve_Ap, Kp, solve_Mp, solve_Rp, bc_idx, bc_val):
+    """y = -Rp^-1 x - Mp^-1 (I + Kp Ap^-1) x;  preconditioners.py:251-262, step by step."""
+    z = x.copy()
+    apply_bcs(z, bc_idx, bc_val)
+    y = solve_Ap(z)
+    z = Kp @ y
+    z = z + x
+    y = solve_Mp(z)
+    z = solve_Rp(x)                    # ksp_Rp.solve(x, z)
+    y = y + z                          # y.axpy(1.0, z)
+    return -y
+
+
+def pcdr_brm2_apply(x, solve_Ap, Kp, solve_Mp, solve_Rp, bc_idx, bc_val):
+    """y = -Rp^-1 x - (I + Ap^-1 Kp) Mp^-1 x;  preconditioners.py:284-297."""
+    y = solve_Mp(x)
+    z0 = y.copy()
+    z1 = Kp @ z0
+    apply_bcs(z1, bc_idx, bc_val)
+    z0 = solve_Ap(z1)
+    y = y + z0
+    z0 = solve_Rp(x)                   # ksp_Rp.solve(x, z0)
+    y = y + z0
+    return -y
+
+
 def fieldsplit_upper_apply(x_u, x_p, schur_apply, A01, solve_A00):
     """PCFIELDSPLIT, SCHUR factorisation, UPPER (field_split.py:54-57; PETSc
     fieldsplit.c recalled):
@@ -247,9 +286,14 @@ class PCDPreconditioner:
     """
 
     def __init__(self, prob, ls="direct", amg_u=None, amg_p=None, cheb_steps=5,
-                 ap_its=2, u_its=1):
+                 ap_its=2, u_its=1, pcdr=False, amg_r=None, rp_its=1):
         self.prob = prob
         self.ls = ls
+        self.pcdr = pcdr
+        if pcdr:      # PCDR variants: Rp from the discrete gradient and the velocity mass diagonal
+            self.Rp = build_rp(prob.A01, prob.mu_diag)
+            self.solve_Rp = direct_solver(self.Rp) if ls == "direct" else \
+                (lambda b: richardson(self.Rp, amg_r, b, rp_its))
         P00 = prob.P00 if prob.P00 is not None else prob.A00
         if ls == "direct":
             self.solve_A00 = direct_solver(P00)
@@ -263,6 +307,10 @@ class PCDPreconditioner:
             self.solve_A00 = lambda b: richardson(P00, amg_u, b, u_its)
 
     def schur_apply(self, x_p):
+        if self.pcdr:
+            f = pcdr_brm1_apply if self.prob.variant == "BRM1" else pcdr_brm2_apply
+            return f(x_p, self.solve_Ap, self.prob.Kp, self.solve_Mp, self.solve_Rp, self.prob.bc_idx,
+                     self.prob.bc_val)
         f = brm1_apply if self.prob.variant == "BRM1" else brm2_apply
         return f(x_p, self.solve_Ap, self.prob.Kp, self.solve_Mp, self.prob.bc_idx, self.prob.bc_val)
 

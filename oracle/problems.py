@@ -38,6 +38,7 @@ class PCDProblem:
     is_u: np.ndarray | None = None      # monolithic numbering of the split dofs
     is_p: np.ndarray | None = None
     cheb_bounds: tuple = (0.5, 2.0)
+    mu_diag: np.ndarray | None = None   # diagonal of the velocity mass matrix (1/dt) (u, v), PCDR only
     meta: dict = field(default_factory=dict)
 
     @property
@@ -69,7 +70,7 @@ def interleaved_index_sets(space: fem.TaylorHoodSpace):
 
 def _build(name, space, nu, variant, wind, vel_bc_nodes, vel_bc_vals, pcd_bc_mask,
            inlet_mask_fn=None, idt=0.0, stabilise=False, newton=False, cheb_bounds=None,
-           qorder=3):
+           qorder=3, pcdr=False):
     """Common assembly path.  ``wind``: [n2, d] nodal P2 wind.  ``vel_bc_nodes``:
     P2 node ids with Dirichlet velocity, ``vel_bc_vals``: [len, d]."""
     d = space.dim
@@ -107,8 +108,14 @@ def _build(name, space, nu, variant, wind, vel_bc_nodes, vel_bc_vals, pcd_bc_mas
     # PCD operators (fenapack/assembling.py:151-171)
     Mp = asm.p1_mass(1.0 / nu)
     Kp = asm.p1_convection(wind, 1.0 / nu)
-    if idt != 0.0:
+    mu_diag = None
+    if idt != 0.0 and not pcdr:
+        # PCD for unsteady problems: reaction term in Kp (demo_unsteady-navier-stokes-pcd.py:138)
         Kp = (Kp + asm.p1_mass(idt / nu)).tocsr()
+    if pcdr:
+        # PCDR: Kp stays pure convection, the reaction enters through Rp built from
+        # mu = (1/dt) (u, v) (demo_unsteady-navier-stokes-pcdr.py:137-139); no BCs on mu
+        mu_diag = np.repeat(asm.p2_scalar(mass_coeff=idt).diagonal(), d)
     if variant == "BRM2" and inlet_mask_fn is not None:
         Kp = (Kp - asm.p1_boundary_flux_mass(wind, inlet_mask_fn, 1.0 / nu)).tocsr()
     Kp.sort_indices()
@@ -120,7 +127,7 @@ def _build(name, space, nu, variant, wind, vel_bc_nodes, vel_bc_vals, pcd_bc_mas
         cheb_bounds = (0.5, 2.0) if d == 2 else (0.5, 2.5)
     return PCDProblem(name=name, dim=d, nu=nu, variant=variant, A00=A00, A01=A01, A10=A10,
                       Mp=Mp, Ap=Ap, Kp=Kp, bc_idx=bc_idx, bc_val=np.zeros(bc_idx.size),
-                      b_u=b_u, b_p=b_p, P00=P00, is_u=is_u, is_p=is_p, cheb_bounds=cheb_bounds,
+                      b_u=b_u, b_p=b_p, P00=P00, is_u=is_u, is_p=is_p, cheb_bounds=cheb_bounds, mu_diag=mu_diag,
                       meta={"n2": space.n2, "n1": space.n1, "cells": space.cells.shape[0],
                             "ndofs": space.nu_dofs + space.n1})
 
@@ -164,7 +171,7 @@ def bfs_boundary(space):
 
 
 def backward_facing_step(level=4, nu=0.02, variant="BRM1", wind=None, idt=0.0,
-                         stabilise=False, newton=False):
+                         stabilise=False, newton=False, pcdr=False):
     """One linearised step of the reference BFS problem around ``wind``
     ([n2, 2] nodal values; default: zero wind = Stokes, the first Picard step
     from the zero initial guess of the demo)."""
@@ -176,7 +183,7 @@ def backward_facing_step(level=4, nu=0.02, variant="BRM1", wind=None, idt=0.0,
     pcd_mask = np.isclose(vx, -1.0) if variant == "BRM1" else np.isclose(vx, 5.0)
     return _build(f"bfs_l{level}", space, nu, variant, wind, dirichlet, vals, pcd_mask,
                   inlet_mask_fn=lambda x: np.isclose(x[:, 0], -1.0), idt=idt,
-                  stabilise=stabilise, newton=newton), space
+                  stabilise=stabilise, newton=newton, pcdr=pcdr), space
 
 
 # --------------------------------------------------------------------------

@@ -70,9 +70,9 @@ class BFSModel:
     """Picard-linearised Navier-Stokes on the BFS mesh; ``w`` (monolithic Vec) is
     the current iterate all forms are evaluated at."""
 
-    def __init__(self, level=2, nu=0.02, variant="BRM1"):
+    def __init__(self, level=2, nu=0.02, variant="BRM1", idt=0.0):
         self.space = S = problems.bfs_space(level)
-        self.nu, self.variant = nu, variant
+        self.nu, self.variant, self.idt = nu, variant, idt
         self.asm = fem.Assembler(S)
         self.is_u, self.is_p = problems.interleaved_index_sets(S)
         self.N = S.nu_dofs + S.n1
@@ -84,7 +84,7 @@ class BFSModel:
         vx = S.verts[:, 0]
         mask = np.isclose(vx, -1.0) if variant == "BRM1" else np.isclose(vx, 5.0)
         self.bc_pcd = DirichletDofs(self.is_p[np.flatnonzero(mask)], 0.0)
-        self.K = self.asm.velocity_block(self.asm.p2_scalar(nu=nu))
+        self.K = self.asm.velocity_block(self.asm.p2_scalar(nu=nu, mass_coeff=idt))
         self.A10 = self.asm.divergence()
         self.A01 = self.A10.T.tocsr()
         # permutation split -> monolithic
@@ -146,6 +146,14 @@ class BFSModel:
 
     def mp(self):
         return self._embed_p(self.asm.p1_mass(1.0 / self.nu))
+
+    def mu(self):
+        """Velocity mass matrix (1/dt) (u, v) on the mixed space (PCDR only), no BCs."""
+        Mu = self.asm.velocity_block(self.asm.p2_scalar(mass_coeff=self.idt))
+        c = sp.coo_matrix(Mu)
+        out = sp.coo_matrix((c.data, (self.is_u[c.row], self.is_u[c.col])), shape=(self.N, self.N)).tocsr()
+        out.sort_indices()
+        return out
 
     def ap(self):
         return self._embed_p(self.asm.p1_laplace())

@@ -59,8 +59,11 @@ def test_pcd_form_flags_and_assembler_defaults():
     asm = make_assembler(m)
     assert asm.get_pcd_form("ap").is_constant() and asm.get_pcd_form("mp").is_constant()
     assert not asm.get_pcd_form("kp").is_constant()
+    assert asm.get_pcd_form("gp").phantom and asm.get_pcd_form("gp").is_phantom()
     with pytest.raises(AttributeError):
-        asm.get_pcd_form("fp")
+        asm.get_dolfin_form("fp")
+    with pytest.raises(AttributeError):
+        asm.get_pcd_form("nope")
     with pytest.raises(AttributeError):
         fp.PCDAssembler(m.a, m.L, [], function_space=m.W).pcd_bcs()
     Ap = Mat()
@@ -186,3 +189,49 @@ def test_python_pc_protocol_schur_only_mode():
     assert relerr(y.array, ref) <= 1e-8
     with pytest.raises(ValueError):
         pc.apply(x, x)
+
+
+@pytest.mark.gpu
+def test_pcdr_through_the_python_pc_protocol():
+    """PCDRPC_BRM1 as a python-type PC context (Schur-only mode): Mu and Bt come from the
+    PCDInterface exactly as in reference preconditioners.py:191-206."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from fenapack_b200 import capi
+    from oracle import petsc_algos as pa
+    from util import oracle_hierarchy_from_device, relerr
+    Options.clear()
+    m = BFSModel(level=2, variant="BRM1", idt=5.0)
+    J, b = m._system()
+    ws = -spla.spsolve(J.tocsc(), b)
+    m.w.array[m.is_u] = ws[:m.n_u]
+    m.w.array[m.is_p] = ws[m.n_u:]
+    set_iterative_options("", "BRM1")
+    o = Options("")
+    o.setValue("fieldsplit_p_pc_python_type", "fenapack.PCDRPC_BRM1")
+    for k, v in (("ksp_type", "richardson"), ("ksp_max_it", 1), ("pc_type", "hypre"), ("pc_hypre_type", "boomeramg")):
+        o.setValue("fieldsplit_p_PCD_Rp_" + k, v)
+    asm = fp.PCDAssembler(m.a, m.L, [], None, ap=m.ap, kp=m.kp, mp=m.mp, mu=m.mu, bcs_pcd=m.bc_pcd,
+                          function_space=m.W)
+    A = Mat(m.a())
+    is_u, is_p = dofmap_dofs_is(m.W.sub(0).dofmap()), dofmap_dofs_is(m.W.sub(1).dofmap())
+    pc = PC(prefix="fieldsplit_p_")
+    pc.setFromOptions()
+    ctx = pc.getPythonContext()
+    assert type(ctx).__name__ == "PCDRPC_BRM1"
+    ctx.init_pcd(PCDInterface(asm, A, is_u, is_p, deep_submats=True))
+    pc.setUp()
+    x = Vec(np.random.default_rng(0).standard_normal(is_p.getSize()))
+    y = x.duplicate()
+    pc.apply(x, y)
+    Mp, Ap, Kp, Bt = ctx.mat_Mp.csr, ctx.mat_Ap.csr, ctx.mat_Kp.csr, ctx.mat_Bt.csr
+    Rp = pa.build_rp(Bt, ctx.mat_Mu.csr.diagonal())
+    Hp = oracle_hierarchy_from_device(ctx._ctx, capi.MAT_AP)
+    Hr = oracle_hierarchy_from_device(ctx._ctx, capi.MAT_RP)
+    dinv = 1.0 / Mp.diagonal()
+    idx, vals = ctx.interface.pcd_bc_indices()
+    ref = pa.pcdr_brm1_apply(x.array, lambda r: pa.richardson(Ap, Hp, r, 2), Kp,
+                             lambda r: pa.chebyshev_jacobi(Mp, dinv, r, 0.5, 2.0, 5),
+                             lambda r: pa.richardson(Rp, Hr, r, 1), idx, vals)
+    assert relerr(y.array, ref) <= 1e-8

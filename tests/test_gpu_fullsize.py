@@ -79,11 +79,18 @@ def test_solution_true_residual_and_reproducibility(setup):
 
 
 def test_kronecker_and_general_storage_agree(setup):
-    prob, ctx, make, capi = setup
-    xu, xp, its, _, _ = ctx.solve(prob.b_u, prob.b_p)
-    cg = make({"fnp_kronecker": 0})
+    prob, _, make, capi = setup
+    # tight tolerance: at rtol 1e-6 the two (differently rounded) Krylov processes stop at
+    # solutions that differ by the conditioning of the system, not by the storage format
+    ck = make({"ksp_rtol": 1e-11})
+    xu, xp, its, _, _ = ck.solve(prob.b_u, prob.b_p)
+    ck.close()
+    cg = make({"fnp_kronecker": 0, "ksp_rtol": 1e-11})
     assert cg.block_size(capi.MAT_A00) == 1
     gu, gp, its_g, _, _ = cg.solve(prob.b_u, prob.b_p)
     cg.close()
-    assert abs(its - its_g) <= 2
-    assert relerr(np.concatenate([gu, gp]), np.concatenate([xu, xp])) <= 1e-4     # both solved to rtol 1e-6
+    assert abs(its - its_g) <= 0.1 * its        # ~90 iterations to 1e-11; the rho estimates differ by ~1e-3
+    # the enclosed-flow system is singular in the constant pressure: compare the velocities
+    # and the pressures up to their mean
+    assert relerr(gu, xu) <= 1e-6
+    assert relerr(gp - gp.mean(), xp - xp.mean()) <= 1e-5

@@ -358,7 +358,7 @@ def test_stored_zeros_are_pruned_and_kronecker_detected():
                                                                    np.concatenate([c.col for c in coo]))),
                           shape=pat.shape).tocsr()
     dense.sort_indices()
-    assert dense.nnz > 2.5 * prob.A00.nnz and abs(dense - prob.A00).max() == 0.0
+    assert dense.nnz > 2.0 * prob.A00.nnz and abs(dense - prob.A00).max() == 0.0
     import copy
     pd = copy.copy(prob)
     pd.A00 = dense
@@ -383,3 +383,40 @@ def test_stored_zeros_are_pruned_and_kronecker_detected():
     assert cg.block_size(capi.MAT_A00) == 1
     assert relerr(cg.spmv(capi.MAT_A00, x, prob.n_u), prob.A00 @ x) <= TOL_SPMV
     cg.close()
+
+
+@pytest.mark.parametrize("variant", ["BRM1", "BRM2"])
+def test_pcdr_variants(variant):
+    """PCDRPC_BRM1/2 (reference preconditioners.py:173-298) on the unsteady BFS problem:
+    Rp = Bt^T diag(Mu)^-1 Bt built by the library against PCDInterface._build_approx_Ap
+    restated in the oracle, the extra Rp solve, the Schur apply and the outer solve."""
+    p0, _ = problems.backward_facing_step(3, variant=variant, idt=5.0)
+    x = pa.direct_solver(p0.system_matrix())(p0.rhs())
+    prob, _ = problems.backward_facing_step(3, variant=variant, wind=x[:p0.n_u].reshape(-1, 2), idt=5.0,
+                                            stabilise=True, pcdr=True)
+    ctx = make_context(prob, pcdr=True)
+    Rp = pa.build_rp(prob.A01, prob.mu_diag)
+    rng = np.random.default_rng(8)
+    v = rng.standard_normal(prob.n_p)
+    assert relerr(ctx.spmv(capi.MAT_RP, v, prob.n_p), Rp @ v) <= 1e-12
+    pc = oracle_preconditioner(prob, ctx, pcdr=True)
+    assert relerr(ctx.rp_solve(v), pc.solve_Rp(v)) <= 1e-11
+    y = ctx.schur_apply(v)
+    assert relerr(y, pc.schur_apply(v)) <= TOL_PC
+    # the Rp hierarchy equals the oracle's own set-up on the oracle's own Rp
+    levels, _ = ctx.amg_hierarchy(capi.MAT_RP)
+    H = oamg.build_hierarchy(Rp)
+    assert [l["A"].shape[0] for l in levels] == [l.A.shape[0] for l in H.levels]
+    A, b = prob.system_matrix(), prob.rhs()
+    x_ref, its_ref, hist_ref, _ = pa.fgmres(A, pc, b, rtol=1e-6, restart=150)
+    xu, xp, its, rn, nap = ctx.solve(prob.b_u, prob.b_p)
+    assert abs(its - its_ref) <= 1
+    assert np.linalg.norm(b - A @ np.concatenate([xu, xp])) <= 2e-6 * np.linalg.norm(b)
+    # PCDR needs fewer iterations than PCD with the reaction term in Kp on this problem
+    # (the reference's documentation.rst:134-140 reports 67 vs 126 per time step)
+    pcd, _ = problems.backward_facing_step(3, variant=variant, wind=x[:p0.n_u].reshape(-1, 2), idt=5.0, stabilise=True)
+    c2 = make_context(pcd)
+    _, _, its_pcd, _, _ = c2.solve(pcd.b_u, pcd.b_p)
+    assert its <= its_pcd
+    ctx.close()
+    c2.close()

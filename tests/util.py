@@ -25,10 +25,13 @@ ITERATIVE_OPTIONS = {
 }
 
 
-def make_context(prob, extra_options=None, device=0):
+def make_context(prob, extra_options=None, device=0, pcdr=False):
     ctx = capi.Context(device)
     opts = dict(ITERATIVE_OPTIONS)
-    opts["fieldsplit_p_pc_python_type"] = "fenapack.PCDPC_" + prob.variant
+    opts["fieldsplit_p_pc_python_type"] = ("fenapack.PCDRPC_" if pcdr else "fenapack.PCDPC_") + prob.variant
+    if pcdr:        # demo_unsteady-navier-stokes-pcdr.py:167-170
+        opts.update({"fieldsplit_p_PCD_Rp_ksp_type": "richardson", "fieldsplit_p_PCD_Rp_ksp_max_it": 1,
+                     "fieldsplit_p_PCD_Rp_pc_type": "hypre", "fieldsplit_p_PCD_Rp_pc_hypre_type": "boomeramg"})
     opts["fieldsplit_p_PCD_Mp_ksp_chebyshev_eigenvalues"] = "%r, %r" % tuple(prob.cheb_bounds)
     opts.update(extra_options or {})
     ctx.set_options(opts)
@@ -42,6 +45,8 @@ def make_context(prob, extra_options=None, device=0):
     if prob.P00 is not None:
         ctx.set_matrix(capi.MAT_P00, prob.P00)
     ctx.set_bc(prob.bc_idx, prob.bc_val)
+    if pcdr:
+        ctx.set_mu_diag(prob.mu_diag)
     if prob.is_u is not None:
         ctx.set_index_sets(prob.is_u, prob.is_p)
     ctx.setup()
@@ -66,9 +71,12 @@ def oracle_hierarchy_from_device(ctx, which, smooth_steps=2, eig_ratio=10.0):
     return H
 
 
-def oracle_preconditioner(prob, ctx):
+def oracle_preconditioner(prob, ctx, pcdr=False):
     Hu = oracle_hierarchy_from_device(ctx, capi.MAT_A00)
     Hp = oracle_hierarchy_from_device(ctx, capi.MAT_AP)
+    if pcdr:
+        Hr = oracle_hierarchy_from_device(ctx, capi.MAT_RP)
+        return pa.PCDPreconditioner(prob, "iterative", amg_u=Hu, amg_p=Hp, pcdr=True, amg_r=Hr)
     return pa.PCDPreconditioner(prob, "iterative", amg_u=Hu, amg_p=Hp)
 
 
