@@ -80,7 +80,8 @@ class BFSModel:
         self.w = Vec(np.zeros(self.N))
         dirichlet, vals, _, _, _ = problems.bfs_boundary(S)
         self.bc_u = (2 * dirichlet[:, None] + np.arange(2)[None, :]).ravel()      # split-u numbering
-        self.g_u = vals.ravel()
+        self.g_u_steady = vals.ravel()
+        self.g_u = self.g_u_steady.copy()
         vx = S.verts[:, 0]
         mask = np.isclose(vx, -1.0) if variant == "BRM1" else np.isclose(vx, 5.0)
         self.bc_pcd = DirichletDofs(self.is_p[np.flatnonzero(mask)], 0.0)
@@ -93,6 +94,15 @@ class BFSModel:
                                 shape=(self.N, self.N))
         self.n_u = n_u
         self.split2mono = np.concatenate([self.is_u, self.is_p])
+        # backward Euler: (1/dt) M (u - u0) in the residual (demo_unsteady-navier-stokes-pcd.py:118-127)
+        self.Mu_dt = self.asm.velocity_block(self.asm.p2_scalar(mass_coeff=idt)) if idt else None
+        self.w0 = Vec(np.zeros(self.N))
+
+    def set_time(self, t, t_ramp=1.0):
+        """Inflow ramp of the unsteady demo (demo_unsteady-navier-stokes-pcd.py:80-84):
+        the parabolic profile is scaled by a smooth ramp in time."""
+        f = 1.0 if t >= t_ramp else 0.5 * (1.0 - np.cos(np.pi * t / t_ramp))
+        self.g_u = f * self.g_u_steady
 
     def wind(self):
         return self.w.array[self.is_u].reshape(-1, 2)
@@ -115,6 +125,8 @@ class BFSModel:
         J = self._jacobian_free(stabilised)
         ws = np.concatenate([self.w.array[self.is_u], self.w.array[self.is_p]])
         F = J @ ws
+        if self.Mu_dt is not None:
+            F[:self.n_u] -= self.Mu_dt @ self.w0.array[self.is_u]
         dxbc = ws[self.bc_u] - self.g_u
         lift = np.zeros(self.N)
         lift[self.bc_u] = dxbc

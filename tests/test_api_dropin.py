@@ -235,3 +235,54 @@ def test_pcdr_through_the_python_pc_protocol():
                              lambda r: pa.chebyshev_jacobi(Mp, dinv, r, 0.5, 2.0, 5),
                              lambda r: pa.richardson(Rp, Hr, r, 1), idx, vals)
     assert relerr(y.array, ref) <= 1e-8
+
+
+@pytest.mark.gpu
+def test_unsteady_time_loop_with_per_step_refresh():
+    """cfg3 of BASELINE.json at reduced size: backward Euler on the BFS, ONE solver object
+    for the whole run (wiring once, Fp/velocity values refreshed at every Newton step of
+    every time step -- reference demo_unsteady-navier-stokes-pcd.py:188-208), reaction term
+    (1/dt) in Kp (:138)."""
+    Options.clear()
+    dt = 0.2
+    m = BFSModel(level=2, variant="BRM1", idt=1.0 / dt)
+    set_iterative_options("", "BRM1")
+    kp_steady = m.kp
+
+    def kp_unsteady():        # kp += (1/nu)(1/dt) p q
+        from fem_forms import struct_add
+        return struct_add(kp_steady(), m._embed_p(m.asm.p1_mass((1.0 / dt) / m.nu)))
+    asm = fp.PCDAssembler(m.a, m.L, [], m.a_pc, ap=m.ap, kp=kp_unsteady, mp=m.mp, bcs_pcd=m.bc_pcd,
+                          function_space=m.W)
+    linear_solver = fp.PCDKrylovSolver()
+    linear_solver.parameters["relative_tolerance"] = 1e-6
+    linear_solver.parameters["maximum_iterations"] = 400
+    linear_solver.set_from_options()
+    problem = fp.PCDNonlinearProblem(asm)
+    solver = fp.PCDNewtonSolver(linear_solver)
+    solver.parameters["relative_tolerance"] = 1e-5
+    solver.parameters["absolute_tolerance"] = 1e-9
+    ref = BFSModel(level=2, variant="BRM1", idt=1.0 / dt)
+    newton_its, t = 0, 0.0
+    for step in range(4):
+        t += dt
+        m.set_time(t)
+        ref.set_time(t)
+        its, converged = solver.solve(problem, m.w)
+        assert converged
+        newton_its += its
+        m.w0.array[:] = m.w.array
+        # the same time step with direct linear solves
+        for _ in range(its):
+            J, b = ref._system()
+            dx = spla.spsolve(J.tocsc(), b)
+            ws = np.concatenate([ref.w.array[ref.is_u], ref.w.array[ref.is_p]]) - dx
+            ref.w.array[ref.is_u] = ws[:ref.n_u]
+            ref.w.array[ref.is_p] = ws[ref.n_u:]
+        ref.w0.array[:] = ref.w.array
+        assert np.linalg.norm(m.w.array - ref.w.array) <= 1e-3 * np.linalg.norm(ref.w.array)
+    ksp = linear_solver.ksp()
+    assert ksp._pcd_pc.mat_Kp.state >= newton_its          # one value refresh per Newton step
+    assert solver.krylov_iterations() / newton_its < 120
+    with pytest.raises(RuntimeError):
+        linear_solver.init_pcd(asm)                           # wiring happened exactly once
