@@ -42,6 +42,12 @@ OPTIONS = {
     "fieldsplit_u_ksp_max_it": 1,
     "fieldsplit_u_pc_type": "hypre",
     "fieldsplit_u_pc_hypre_type": "boomeramg",
+    # AMG internals (hypre's are not reproducible; these are the library's knobs): one damped-
+    # Jacobi sweep before and after the coarse correction.  Measured on this workload
+    # (profiles/r01_tuning_sweep.md): 21 iterations either way, 55.5 ms instead of 75.2 ms
+    # with the library default of 2 Chebyshev steps.
+    "fieldsplit_u_pc_amg_smooth_steps": 1,
+    "fieldsplit_p_PCD_Ap_pc_amg_smooth_steps": 1,
     "fieldsplit_p_PCD_Ap_ksp_type": "richardson",
     "fieldsplit_p_PCD_Ap_ksp_max_it": 2,
     "fieldsplit_p_PCD_Ap_pc_type": "hypre",
@@ -68,6 +74,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="skip e2e/cpu legs (for ncu runs)")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="extra library option (PETSc-style name), e.g. fieldsplit_u_pc_amg_smooth_steps=3")
     return ap.parse_args()
 
 
@@ -82,7 +90,7 @@ def mesh_size(args, world):
 def workload_name(args, dims, kind, variant, ndofs):
     return (f"{'lid-driven cavity' if kind == 'cavity' else 'channel'} 3D P2/P1 Oseen, {dims[0]}x{dims[1]}x{dims[2]} bricks x6 tets, "
             f"{ndofs} dofs, nu={args.nu}, PCD {variant}, FGMRES(150) rtol 1e-6, "
-            "u: richardson x1 + SA-AMG V(2,2) Chebyshev-Jacobi, Ap: richardson x2 + SA-AMG, Mp: chebyshev x5 + jacobi")
+            "u: richardson x1 + SA-AMG V(1,1) damped Jacobi, Ap: richardson x2 + SA-AMG V(1,1), Mp: chebyshev x5 + jacobi")
 
 
 # ---------------------------------------------------------------------------
@@ -234,6 +242,9 @@ def b200_arm(args):
         ctx = capi.Context(local)
     opts = dict(OPTIONS)
     opts["fieldsplit_p_pc_python_type"] = "fenapack.PCDPC_" + variant
+    for kv in args.opt:
+        k, _, v = kv.partition("=")
+        opts[k] = v
     ctx.set_options(opts)
     if "FNP_OVERLAP" in os.environ:
         ctx.set_option("fnp_halo_overlap", os.environ["FNP_OVERLAP"])
@@ -315,6 +326,8 @@ def b200_arm(args):
         "final_rel_residual": final_rel, "clocks": clocks, "gpu_launches": int(launches),
         "setup": {"generate_s": t_gen, "upload_s": t_upload, "fnp_setup_s": t_setup},
     }
+    if args.opt:
+        result["config"]["extra_options"] = list(args.opt)
 
     if not args.profile_only:
         # ---- e2e: the C-ABI call with HOST (pinned) vectors, copies inside the timed region ----

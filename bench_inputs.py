@@ -106,18 +106,25 @@ class BoxTaylorHood:
 
 
 def _coo_to_csr(rows, cols, vals, nrows_local, row0, ncols):
-    """Sum duplicates; returns numpy (rowptr int32, col int32, val f64) of local rows."""
+    """Sum duplicates; returns numpy (rowptr int32, col int32, val f64) of local rows.
+    Deterministic: duplicates are accumulated in a fixed order (stable sort, then one
+    scatter pass per duplicate rank -- no atomics), so that repeated runs assemble
+    bit-identical operators and the solver's iteration counts are reproducible."""
     key = (rows - row0) * ncols + cols
-    key, order = torch.sort(key)
+    key, order = torch.sort(key, stable=True)
     vals = vals[order]
-    ukey, inv = torch.unique_consecutive(key, return_inverse=True)
+    ukey, inv, counts = torch.unique_consecutive(key, return_inverse=True, return_counts=True)
+    first = torch.cumsum(counts, 0) - counts
+    rank = torch.arange(key.numel(), device=key.device) - first[inv]
     out = torch.zeros(ukey.numel(), dtype=torch.float64, device=vals.device)
-    out.index_add_(0, inv, vals)
+    for r in range(int(counts.max().item()) if key.numel() else 0):
+        sel = torch.nonzero(rank == r, as_tuple=True)[0]
+        out[inv[sel]] += vals[sel]
     r = ukey // ncols
     c = ukey - r * ncols
-    counts = torch.bincount(r, minlength=nrows_local)
+    cnt = torch.bincount(r, minlength=nrows_local)
     rowptr = torch.zeros(nrows_local + 1, dtype=torch.int64, device=vals.device)
-    rowptr[1:] = torch.cumsum(counts, 0)
+    rowptr[1:] = torch.cumsum(cnt, 0)
     return rowptr.to(torch.int32).cpu().numpy(), c.to(torch.int32).cpu().numpy(), out.cpu().numpy()
 
 

@@ -210,6 +210,8 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
     else throw Error(FNP_ERR_OPTION, "option fnp_spmv_kernel: auto | csr | sell (takes effect at fnp_set_pattern)");
   } else if (name == "fnp_halo_p2p") {
     c.p2p = parse_int(name, v);
+  } else if (name == "fnp_sell_max_mean_row") {
+    c.sell_max_mean_row = parse_real(name, v);
   } else if (name == "fnp_prune_zeros") {
     c.prune = parse_int(name, v);
   } else if (name == "fnp_kronecker") {

@@ -350,6 +350,7 @@ struct Ctx {
   DevCsr rp;
   DevHierarchy amg_rp;
   int spmv_mode = 0;            // 0 auto (by row-length histogram), 1 CSR vector kernel always, 2 SELL always
+  double sell_max_mean_row = 64.0;   // auto: operators with a longer mean row keep CSR + sub-warp per row
   int timers_on = 0;            // 0 off, 1 stage timers, 2 also one timer per SpMV launch
 
   // operators

@@ -290,7 +290,7 @@ void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &
   // format choice from the row-length histogram: thread-per-row SELL needs many short
   // rows; long rows (dense coarse levels, the divergence block) keep CSR + one
   // sub-warp per row, which already has enough loads in flight per row
-  const bool short_rows = A.mean_row < 64.0 && maxrow <= 8.0 * std::max(8.0, A.mean_row) && h.nrows >= 4096;
+  const bool short_rows = A.mean_row < c.sell_max_mean_row && maxrow <= 8.0 * std::max(8.0, A.mean_row) && h.nrows >= 4096;
   const bool use_sell = c.spmv_mode == 2 || (c.spmv_mode == 0 && short_rows);
   if (use_sell) {
     build_sell(c, A, h, n_own_split);
