@@ -42,12 +42,6 @@ OPTIONS = {
     "fieldsplit_u_ksp_max_it": 1,
     "fieldsplit_u_pc_type": "hypre",
     "fieldsplit_u_pc_hypre_type": "boomeramg",
-    # AMG internals (hypre's are not reproducible; these are the library's knobs): one damped-
-    # Jacobi sweep before and after the coarse correction.  Measured on this workload
-    # (profiles/r01_tuning_sweep.md): 21 iterations either way, 55.5 ms instead of 75.2 ms
-    # with the library default of 2 Chebyshev steps.
-    "fieldsplit_u_pc_amg_smooth_steps": 1,
-    "fieldsplit_p_PCD_Ap_pc_amg_smooth_steps": 1,
     "fieldsplit_p_PCD_Ap_ksp_type": "richardson",
     "fieldsplit_p_PCD_Ap_ksp_max_it": 2,
     "fieldsplit_p_PCD_Ap_pc_type": "hypre",
@@ -90,7 +84,7 @@ def mesh_size(args, world):
 def workload_name(args, dims, kind, variant, ndofs):
     return (f"{'lid-driven cavity' if kind == 'cavity' else 'channel'} 3D P2/P1 Oseen, {dims[0]}x{dims[1]}x{dims[2]} bricks x6 tets, "
             f"{ndofs} dofs, nu={args.nu}, PCD {variant}, FGMRES(150) rtol 1e-6, "
-            "u: richardson x1 + SA-AMG V(1,1) damped Jacobi, Ap: richardson x2 + SA-AMG V(1,1), Mp: chebyshev x5 + jacobi")
+            "u: richardson x1 + SA-AMG V(2,2) Chebyshev-Jacobi, Ap: richardson x2 + SA-AMG, Mp: chebyshev x5 + jacobi")
 
 
 # ---------------------------------------------------------------------------
