@@ -525,6 +525,7 @@ int fnp_set_stream(fnp_context *ctx, void *cuda_stream) {
   FNP_API_BEGIN
   CTX(ctx);
   FNP_CUDA(cudaStreamSynchronize(c.stream));
+  c.drop_graph();                       // the captured apply belongs to the old stream
   if (c.own_stream) cudaStreamDestroy(c.stream);
   c.stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   c.own_stream = false;

@@ -48,12 +48,12 @@ void solve_fgmres(Ctx &c, const double *b, double *x, int32_t *its_out, double *
   FNP_REQUIRE(c.is_setup, FNP_ERR_STATE, "fnp_solve before fnp_setup");
   const int64_t n = c.n_u + c.n_p;
   const int m = c.restart;
-  FNP_REQUIRE(m >= 1 && m <= 190, FNP_ERR_OPTION, "ksp_gmres_restart must be in [1, 190]");
+  FNP_REQUIRE(m >= 1 && m <= 990, FNP_ERR_OPTION, "ksp_gmres_restart must be in [1, 990]");
   c.kr_w.ensure((size_t)n);
-  c.red_out.ensure(256);
+  c.red_out.ensure(1024);
   if (!c.pinned) {
-    FNP_CUDA(cudaMallocHost(reinterpret_cast<void **>(&c.pinned), 256 * sizeof(double)));
-    c.pinned_n = 256;
+    FNP_CUDA(cudaMallocHost(reinterpret_cast<void **>(&c.pinned), 1024 * sizeof(double)));
+    c.pinned_n = 1024;
   }
   Basis V(c.V, n, m + 1), Z(c.Z, n, m + 1);
   double *w = c.kr_w.p;

@@ -66,7 +66,7 @@ static void inner_solve(Ctx &c, const InnerOpts &o, const DevCsr &A, DevHierarch
     case KSP_CG: {
       // preconditioned CG, fixed iteration count, scalars stay on the device
       double *r = w0, *z = w1, *p = w2, *q = w3;
-      double *rz = c.red_out.p + 200, *rz2 = c.red_out.p + 201, *pq = c.red_out.p + 202;
+      double *rz = c.red_out.p + 1000, *rz2 = c.red_out.p + 1001, *pq = c.red_out.p + 1002;   // above the Hessenberg column
       vec_zero(c, n, x);
       vec_copy(c, n, b, r);
       apply_inner_pc(c, o, A, H, r, z);
@@ -252,7 +252,7 @@ void setup_all(Ctx &c) {
   FNP_REQUIRE(c.variant >= 1 && c.variant <= 4, FNP_ERR_STATE, "PCD variant not set");
   for (auto &b : c.p_w) b.ensure((size_t)c.n_p);
   for (auto &b : c.u_w) b.ensure((size_t)c.n_u);
-  c.red_out.ensure(256);
+  c.red_out.ensure(1024);
   c.red_partial.ensure((size_t)c.num_sms * 4 * 200);     // sized once: no allocation inside the hot path
   const int uidx = c.velocity_pc_index();
   // AMG hierarchies (Ap: once; velocity block: whenever its values changed)
