@@ -164,6 +164,9 @@ static void set_inner_option(InnerOpts &o, const std::string &full, const std::s
     FNP_REQUIRE(o.amg.smooth_steps >= 1, FNP_ERR_OPTION, "option " + full + ": must be >= 1");
   } else if (key == "pc_amg_prolongator_truncation") {
     o.amg.p_trunc = parse_real(full, v);
+  } else if (key == "pc_amg_lag") {
+    o.amg.lag = parse_int(full, v);
+    FNP_REQUIRE(o.amg.lag >= 1, FNP_ERR_OPTION, "option " + full + ": must be >= 1");
   } else if (key == "pc_amg_replicate_size") {
     o.amg.replicate_size = parse_int(full, v);
   } else if (key == "pc_amg_coarse_drop") {

@@ -228,6 +228,8 @@ struct AmgParams {
   int smooth_steps = 2;
   double eig_ratio = 10.0;
   double omega_scale = 4.0 / 3.0;
+  int lag = 1;                 // rebuild the coarse levels only at every lag-th value refresh (level 0 always
+                               // follows the new matrix) -- the role of PETSc's -pc_gamg_reuse_interpolation
   double p_trunc = 0.2;        // drop prolongator entries below p_trunc*max|row|, rescale to the row sum
   int64_t replicate_size = 0;        // multi-rank, > 0: levels with <= this many (global) rows are gathered and
                                      // coarsened/applied redundantly on every rank.  Off by default: +6 % at N=2
@@ -377,6 +379,7 @@ struct Ctx {
   bool is_setup = false;
 
   DevHierarchy amg_u, amg_ap;
+  int amg_u_age = 0;            // value refreshes since the velocity hierarchy was last rebuilt
 
   // work space
   DevBuf<double> p_w[7];      // pressure-sized work vectors

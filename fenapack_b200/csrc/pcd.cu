@@ -257,7 +257,18 @@ void setup_all(Ctx &c) {
   const int uidx = c.velocity_pc_index();
   // AMG hierarchies (Ap: once; velocity block: whenever its values changed)
   if (c.opt_ap.pc == PC_AMG && (c.dirty[FNP_MAT_AP] || !c.amg_ap.built)) build_amg(c, FNP_MAT_AP, c.amg_ap, c.opt_ap.amg);
-  if (have_u && c.opt_u.pc == PC_AMG && (c.dirty[uidx] || !c.amg_u.built)) build_amg(c, uidx, c.amg_u, c.opt_u.amg);
+  if (have_u && c.opt_u.pc == PC_AMG && (c.dirty[uidx] || !c.amg_u.built)) {
+    // lagged refresh: level 0 aliases the context's operator and its Jacobi diagonal, so it
+    // always follows the new values; the coarse levels may be kept for `lag` refreshes
+    const bool same_shape = c.amg_u.built && !c.amg_u.levels.empty() && c.amg_u.levels[0].Ap == &c.dmat[uidx] &&
+                            c.amg_u.host.levels[0].A.nrows == c.dmat[uidx].nrows;
+    if (same_shape && c.amg_u_age + 1 < c.opt_u.amg.lag) {
+      ++c.amg_u_age;
+    } else {
+      build_amg(c, uidx, c.amg_u, c.opt_u.amg);
+      c.amg_u_age = 0;
+    }
+  }
   if (c.variant >= 3) {
     // PCDR: Rp = Bt^T diag(Mu)^-1 Bt with Bt = A01 (PCDInterface._build_approx_Ap,
     // field_split_backend.py:142-166), rebuilt when A01 or Mu changed

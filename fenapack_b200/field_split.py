@@ -28,7 +28,7 @@ from .utils import allow_only_one_call
 
 _OUTER_KEYS = ("ksp_type", "ksp_gmres_restart", "ksp_rtol", "ksp_atol", "ksp_max_it")
 _U_KEYS = ("ksp_type", "ksp_max_it", "pc_type", "pc_hypre_type", "pc_amg_threshold", "pc_amg_levels",
-           "pc_amg_coarse_size", "pc_amg_smooth_steps", "pc_amg_eig_ratio", "pc_amg_coarse_drop", "pc_amg_prolongator_truncation", "pc_amg_replicate_size")
+           "pc_amg_coarse_size", "pc_amg_smooth_steps", "pc_amg_eig_ratio", "pc_amg_coarse_drop", "pc_amg_prolongator_truncation", "pc_amg_replicate_size", "pc_amg_lag")
 
 
 def dofmap_dofs_is(dofmap):

@@ -97,7 +97,8 @@ int fnp_synchronize(fnp_context *ctx);
  *   fieldsplit_p_PCD_Mp_ksp_type chebyshev, ..._ksp_max_it, ..._ksp_chebyshev_eigenvalues "lo, hi",
  *   ..._pc_type jacobi
  *   <prefix>pc_amg_threshold, pc_amg_levels, pc_amg_coarse_size, pc_amg_smooth_steps,
- *   pc_amg_eig_ratio, pc_amg_prolongator_truncation, pc_amg_coarse_drop for the prefixes fieldsplit_u_ and fieldsplit_p_PCD_Ap_
+ *   pc_amg_eig_ratio, pc_amg_prolongator_truncation, pc_amg_coarse_drop, pc_amg_replicate_size,
+ *   pc_amg_lag (velocity block: rebuild the coarse levels at every lag-th refresh only) for the prefixes fieldsplit_u_ and fieldsplit_p_PCD_Ap_
  * "hypre"/"boomeramg"/"gamg" are accepted as aliases of amg (the smoothed-
  * aggregation hierarchy of this library).  Unknown names -> FNP_ERR_OPTION. */
 int fnp_set_option(fnp_context *ctx, const char *name, const char *value);

@@ -420,3 +420,29 @@ def test_pcdr_variants(variant):
     assert its <= its_pcd
     ctx.close()
     c2.close()
+
+
+def test_lagged_hierarchy_refresh():
+    """pc_amg_lag: after a value refresh the coarse levels may be kept (level 0 follows
+    the new matrix); the solve must still converge in about as many iterations."""
+    p0, _ = problems.backward_facing_step(3, variant="BRM1")
+    x = pa.direct_solver(p0.system_matrix())(p0.rhs())
+    p1, _ = problems.backward_facing_step(3, variant="BRM1", wind=0.5 * x[:p0.n_u].reshape(-1, 2))
+    p2, _ = problems.backward_facing_step(3, variant="BRM1", wind=x[:p0.n_u].reshape(-1, 2))
+    its = {}
+    for lag in (1, 3):
+        ctx = make_context(p1, {"fieldsplit_u_pc_amg_lag": lag})
+        levels_before, _ = ctx.amg_hierarchy(capi.MAT_A00)
+        ctx.set_values(capi.MAT_A00, p2.A00.data)
+        ctx.set_values(capi.MAT_KP, p2.Kp.data)
+        ctx.setup()
+        levels_after, _ = ctx.amg_hierarchy(capi.MAT_A00)
+        a, b_ = levels_after[1]["A"], levels_before[1]["A"]
+        changed = a.shape != b_.shape or a.nnz != b_.nnz or abs(a - b_).max() > 0
+        assert changed == (lag == 1)                      # lag 3: coarse levels kept
+        xu, xp, n, rn, _ = ctx.solve(p2.b_u, p2.b_p)
+        A, b = p2.system_matrix(), p2.rhs()
+        assert np.linalg.norm(b - A @ np.concatenate([xu, xp])) <= 2e-6 * np.linalg.norm(b)
+        its[lag] = n
+        ctx.close()
+    assert its[3] <= 1.5 * its[1]                        # stale coarse levels cost a few iterations (54 -> 67 here)
