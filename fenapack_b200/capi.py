@@ -250,9 +250,17 @@ class Context:
         _check(self._lib.fnp_pc_apply(self._h, _ptr(x_u), _ptr(x_p), _ptr(y_u), _ptr(y_p), 0))
         return y_u, y_p
 
-    def solve(self, b_u, b_p):
+    def solve(self, b_u, b_p, out=None):
+        """FGMRES solve with host vectors.  `out=(x_u, x_p)` writes the solution into caller-owned
+        (e.g. pinned) float64 arrays instead of fresh ones."""
         b_u, b_p = _f64(b_u), _f64(b_p)
-        x_u, x_p = np.empty(self.n_u), np.empty(self.n_p)
+        if out is None:
+            x_u, x_p = np.empty(self.n_u), np.empty(self.n_p)
+        else:
+            x_u, x_p = out
+            for v, n in ((x_u, self.n_u), (x_p, self.n_p)):
+                if v.dtype != np.float64 or not v.flags.c_contiguous or v.size != n:
+                    raise ValueError("out arrays must be contiguous float64 of the local block sizes")
         its, nap, rn = C.c_int32(), C.c_int32(), C.c_double()
         _check(self._lib.fnp_solve(self._h, _ptr(b_u), _ptr(b_p), _ptr(x_u), _ptr(x_p), 0,
                                    C.byref(its), C.byref(rn), C.byref(nap)))

@@ -213,6 +213,11 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
     else throw Error(FNP_ERR_OPTION, "option fnp_spmv_kernel: auto | csr | sell (takes effect at fnp_set_pattern)");
   } else if (name == "fnp_halo_p2p") {
     c.p2p = parse_int(name, v);
+  } else if (name == "fnp_sell_gather") {
+    c.sell_gather = (int)parse_int(name, v);
+    c.drop_graph();
+  } else if (name == "fnp_sell_sigma") {
+    c.sell_sigma = std::max(32, (int)parse_int(name, v) / 32 * 32);
   } else if (name == "fnp_sell_max_mean_row") {
     c.sell_max_mean_row = parse_real(name, v);
   } else if (name == "fnp_prune_zeros") {
@@ -341,7 +346,7 @@ static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t 
     HostCsr loc = h;
     std::shared_ptr<HaloPlan> plan = build_halo(c, loc, begins, nullptr);
     const int64_t n_own_cols = begins[c.rank + 1] - begins[c.rank];
-    csr_upload_pattern(c, d, loc, names[which], (c.overlap || c.p2p) ? n_own_cols : -1, bs);
+    csr_upload_pattern(c, d, loc, names[which], (c.overlap || c.p2p) ? n_own_cols : -1, bs, n_own_cols);
     d.halo = (plan && bs > 1) ? expand_plan(c, *plan, bs) : plan;
     d.ncols_own = (int32_t)n_own_cols;
     d.nghost = plan ? plan->nghost : 0;

@@ -186,7 +186,10 @@ struct EpiCheb {             // out = add + c0 p0 + c1 p1 + c2 dinv (b - A p1)  
 // Upload one operator: picks the storage format from the row-length histogram
 // (SELL-32-sigma for short rows, CSR + sub-warp-per-row kernel for long rows).
 // `val` may be null (pattern only); csr_set_values refreshes the numbers later.
-void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag, int64_t n_own_split = -1, int bs = 1);
+// n_own_split >= 0: rows with a ghost column go to a separate boundary part; n_own_cols: number of
+// owned columns when the column space is [owned | ghost] (-1: all owned)
+void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag, int64_t n_own_split = -1, int bs = 1,
+                        int64_t n_own_cols = -1);
 void csr_set_values(Ctx &c, DevCsr &A, const HostCsr &pattern, const double *val, bool want_dinv);
 void spmv_store(Ctx &c, const DevCsr &A, const double *x, double *y);
 void spmv_axpby(Ctx &c, const DevCsr &A, const double *x, double a, double b, const double *z, double *y);
@@ -352,6 +355,8 @@ struct Ctx {
   DevCsr rp;
   DevHierarchy amg_rp;
   int spmv_mode = 0;            // 0 auto (by row-length histogram), 1 CSR vector kernel always, 2 SELL always
+  int sell_gather = 15;         // SELL kernel variant bits (kernels.cu): 1 wide gathers, 2 six CTAs/SM, 4 L2 prefetch, 8 wide epilogue
+  int sell_sigma = 1024;        // SELL sorting window (rows)
   double sell_max_mean_row = 64.0;   // auto: operators with a longer mean row keep CSR + sub-warp per row
   int timers_on = 0;            // 0 off, 1 stage timers, 2 also one timer per SpMV launch
 

@@ -56,6 +56,22 @@ __device__ __forceinline__ const double *gather_ptr(const double *__restrict__ x
   return c < nown ? x + (int64_t)BS * c : xg + (int64_t)BS * (c - nown);
 }
 
+// The three components of node c with two 16-byte loads instead of three 8-byte ones: the
+// 24-byte group starts either on a 16-byte boundary (take lo.x lo.y hi.x) or 8 bytes past one
+// (take lo.y hi.x hi.y).  Every gather instruction of a warp touches the same cache lines whatever
+// its width, so the LSU wavefront count of the gather -- the limiter of the Kronecker kernel,
+// profiles/r01_spmv_kernel_choice.md -- drops by a third.  The wide loads read 8 bytes beside the
+// group: slices that reference the first or last node of the owned vector or of the ghost buffer
+// are flagged at build time (bit 0 of their slice pointer) and take the scalar loads.
+__device__ __forceinline__ void gather3_wide(const double *__restrict__ p, double &a0, double &a1, double &a2) {
+  const bool odd = (reinterpret_cast<uintptr_t>(p) & 8) != 0;
+  const double2 *q = reinterpret_cast<const double2 *>(p - (odd ? 1 : 0));
+  const double2 lo = __ldg(q), hi = __ldg(q + 1);
+  a0 = odd ? lo.y : lo.x;
+  a1 = odd ? hi.x : lo.y;
+  a2 = odd ? hi.y : hi.x;
+}
+
 template <int LANES, int BS, class Epi>
 __global__ void __launch_bounds__(256)
 spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
@@ -115,18 +131,139 @@ spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__rest
 // the padding stays at a few per cent.
 // ---------------------------------------------------------------------------
 constexpr int SELL_C = 32;
-constexpr int SELL_SIGMA = 1024;
+constexpr int SELL_NARROW = 1;   // flag in bit 0 of a slice pointer (pointers are multiples of 32)
 
-template <int BS, class Epi>
-__global__ void __launch_bounds__(256)
+// Per-thread sums of one SELL row (entries k = 0 .. len-1 at stride 32).  WIDE selects the
+// 16-byte gathers (BS == 3 only); products and their order are the same in both variants.
+template <int BS, bool WIDE>
+__device__ __forceinline__ void sell_row_sums(const int32_t *__restrict__ cp, const double *__restrict__ vp, int len,
+                                              const double *__restrict__ x, const double *__restrict__ xg, int nown,
+                                              double (&out)[BS]) {
+  double s0[BS], s1[BS];
+#pragma unroll
+  for (int b = 0; b < BS; ++b) s0[b] = s1[b] = 0.0;
+  int k = 0;
+  for (; k + 4 <= len; k += 4) {
+    const int c0 = __ldcs(cp + (k + 0) * SELL_C), c1 = __ldcs(cp + (k + 1) * SELL_C);
+    const int c2 = __ldcs(cp + (k + 2) * SELL_C), c3 = __ldcs(cp + (k + 3) * SELL_C);
+    const double v0 = __ldcs(vp + (k + 0) * SELL_C), v1 = __ldcs(vp + (k + 1) * SELL_C);
+    const double v2 = __ldcs(vp + (k + 2) * SELL_C), v3 = __ldcs(vp + (k + 3) * SELL_C);
+    const double *p0 = gather_ptr<BS>(x, xg, nown, c0), *p1 = gather_ptr<BS>(x, xg, nown, c1);
+    const double *p2 = gather_ptr<BS>(x, xg, nown, c2), *p3 = gather_ptr<BS>(x, xg, nown, c3);
+    double x0[BS], x1[BS], x2[BS], x3[BS];
+    if constexpr (WIDE) {
+      gather3_wide(p0, x0[0], x0[1], x0[2]);
+      gather3_wide(p1, x1[0], x1[1], x1[2]);
+      gather3_wide(p2, x2[0], x2[1], x2[2]);
+      gather3_wide(p3, x3[0], x3[1], x3[2]);
+    } else {
+#pragma unroll
+      for (int b = 0; b < BS; ++b) {
+        x0[b] = __ldg(p0 + b);
+        x1[b] = __ldg(p1 + b);
+        x2[b] = __ldg(p2 + b);
+        x3[b] = __ldg(p3 + b);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < BS; ++b) {
+      s0[b] += v0 * x0[b];
+      s1[b] += v1 * x1[b];
+      s0[b] += v2 * x2[b];
+      s1[b] += v3 * x3[b];
+    }
+  }
+  for (; k < len; ++k) {
+    const double v0 = __ldcs(vp + k * SELL_C);
+    const double *p0 = gather_ptr<BS>(x, xg, nown, __ldcs(cp + k * SELL_C));
+    double x0[BS];
+    if constexpr (WIDE) {
+      gather3_wide(p0, x0[0], x0[1], x0[2]);
+    } else {
+#pragma unroll
+      for (int b = 0; b < BS; ++b) x0[b] = __ldg(p0 + b);
+    }
+#pragma unroll
+    for (int b = 0; b < BS; ++b) s0[b] += v0 * x0[b];
+  }
+#pragma unroll
+  for (int b = 0; b < BS; ++b) out[b] = s0[b] + s1[b];
+}
+
+// three consecutive doubles at p (coherent loads: the operand may be written by other rows
+// of the same launch, e.g. z aliasing y); `wide` as in gather3_wide
+__device__ __forceinline__ void load3(const double *p, bool wide, double (&o)[3]) {
+  if (wide) {
+    const bool odd = (reinterpret_cast<uintptr_t>(p) & 8) != 0;
+    const double2 *q = reinterpret_cast<const double2 *>(p - (odd ? 1 : 0));
+    const double2 lo = q[0], hi = q[1];
+    o[0] = odd ? lo.y : lo.x;
+    o[1] = odd ? hi.x : lo.y;
+    o[2] = odd ? hi.y : hi.x;
+  } else {
+    o[0] = p[0];
+    o[1] = p[1];
+    o[2] = p[2];
+  }
+}
+__device__ __forceinline__ void epilogue3(const EpiStore &e, int r, const double (&s)[3], bool) {
+#pragma unroll
+  for (int b = 0; b < 3; ++b) e.y[3 * r + b] = s[b];
+}
+__device__ __forceinline__ void epilogue3(const EpiAxpby &e, int r, const double (&s)[3], bool wide) {
+  double z[3];
+  load3(e.z + 3 * r, wide, z);
+#pragma unroll
+  for (int b = 0; b < 3; ++b) e.y[3 * r + b] = e.a * s[b] + e.b * z[b];
+}
+__device__ __forceinline__ void epilogue3(const EpiCheb &e, int r, const double (&s)[3], bool wide) {
+  double p1[3], di[3], bb[3], v[3];
+  load3(e.p1 + 3 * r, wide, p1);
+  load3(e.dinv + 3 * r, wide, di);
+  load3(e.b + 3 * r, wide, bb);
+#pragma unroll
+  for (int b = 0; b < 3; ++b) v[b] = e.c1 * p1[b] + e.c2 * di[b] * (bb[b] - s[b]);
+  if (e.p0) {
+    double t[3];
+    load3(e.p0 + 3 * r, wide, t);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) v[b] += e.c0 * t[b];
+  }
+  if (e.add) {
+    double t[3];
+    load3(e.add + 3 * r, wide, t);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) v[b] += t[b];
+  }
+#pragma unroll
+  for (int b = 0; b < 3; ++b) e.out[3 * r + b] = v[b];
+}
+
+__device__ __forceinline__ void sell_prefetch(const int32_t *__restrict__ col, const double *__restrict__ val, int base, int len) {
+  // pull a slice's whole (col, val) stream into L2 with two bulk prefetches: the dependent
+  // col -> gather chain then waits on L2, not on HBM
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(col + base), "r"(len * SELL_C * 4) : "memory");
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(val + base), "r"(len * SELL_C * 8) : "memory");
+}
+
+// VAR bits (option fnp_sell_gather): 1 16-byte gathers (BS == 3), 2 six CTAs per SM (40 registers),
+// 4 L2 bulk prefetch of the slice stream, 8 16-byte loads in the epilogue (BS == 3).
+// Measured on A00 = S (x) I_3 of the 64^3 cavity (profiles/r01_spmv_kernel_choice.md): 0.247 ms
+// with none, 0.178 ms with the prefetch alone, 0.170 ms with all.  A persistent variant (warps
+// striding over slices, next slice prefetched) was measured 2x slower and is not kept.
+template <int BS, class Epi, int VAR>
+__global__ void __launch_bounds__(256, (VAR & 2) ? 6 : 0)
 spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t *__restrict__ col,
                  const double *__restrict__ val, const int32_t *__restrict__ perm, const double *__restrict__ x,
                  const double *__restrict__ xg, int nown, Epi epi) {
   const int slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (slice >= nslices) return;
-  const int base = __ldg(sl_ptr + slice);
-  const int len = (__ldg(sl_ptr + slice + 1) - base) >> 5;
+  const int raw = __ldg(sl_ptr + slice);
+  const int base = raw & ~(SELL_C - 1);
+  const bool narrow = (raw & SELL_NARROW) != 0;     // slice touches an end of a vector: scalar loads
+  const int len = ((__ldg(sl_ptr + slice + 1) & ~(SELL_C - 1)) - base) >> 5;
+  if ((VAR & 4) && lane == 0 && len > 0) sell_prefetch(col, val, base, len);
   const int row = __ldg(perm + slice * SELL_C + lane);
   const int32_t *cp = col + base + lane;
   const double *vp = val + base + lane;
@@ -146,34 +283,18 @@ spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t 
     for (; k < len; ++k) s0 += __ldcs(vp + k * SELL_C) * __ldg(gather_ptr<1>(x, xg, nown, __ldcs(cp + k * SELL_C)));
     if (row >= 0) epilogue(epi, row, (s0 + s1) + (s2 + s3));
   } else {
-    double s0[BS], s1[BS];
-#pragma unroll
-    for (int b = 0; b < BS; ++b) s0[b] = s1[b] = 0.0;
-    int k = 0;
-    for (; k + 4 <= len; k += 4) {
-      const int c0 = __ldcs(cp + (k + 0) * SELL_C), c1 = __ldcs(cp + (k + 1) * SELL_C);
-      const int c2 = __ldcs(cp + (k + 2) * SELL_C), c3 = __ldcs(cp + (k + 3) * SELL_C);
-      const double v0 = __ldcs(vp + (k + 0) * SELL_C), v1 = __ldcs(vp + (k + 1) * SELL_C);
-      const double v2 = __ldcs(vp + (k + 2) * SELL_C), v3 = __ldcs(vp + (k + 3) * SELL_C);
-      const double *p0 = gather_ptr<BS>(x, xg, nown, c0), *p1 = gather_ptr<BS>(x, xg, nown, c1);
-      const double *p2 = gather_ptr<BS>(x, xg, nown, c2), *p3 = gather_ptr<BS>(x, xg, nown, c3);
-#pragma unroll
-      for (int b = 0; b < BS; ++b) {
-        s0[b] += v0 * __ldg(p0 + b);
-        s1[b] += v1 * __ldg(p1 + b);
-        s0[b] += v2 * __ldg(p2 + b);
-        s1[b] += v3 * __ldg(p3 + b);
-      }
-    }
-    for (; k < len; ++k) {
-      const double v0 = __ldcs(vp + k * SELL_C);
-      const double *p0 = gather_ptr<BS>(x, xg, nown, __ldcs(cp + k * SELL_C));
-#pragma unroll
-      for (int b = 0; b < BS; ++b) s0[b] += v0 * __ldg(p0 + b);
-    }
+    double s[BS];
+    if (BS == 3 && (VAR & 1) && !narrow)
+      sell_row_sums<BS, BS == 3>(cp, vp, len, x, xg, nown, s);
+    else
+      sell_row_sums<BS, false>(cp, vp, len, x, xg, nown, s);
     if (row >= 0) {
+      if constexpr (BS == 3 && (VAR & 8) != 0) {
+        epilogue3(epi, row, s, !narrow);
+      } else {
 #pragma unroll
-      for (int b = 0; b < BS; ++b) epilogue(epi, BS * row + b, s0[b] + s1[b]);
+        for (int b = 0; b < BS; ++b) epilogue(epi, BS * row + b, s[b]);
+      }
     }
   }
 }
@@ -187,7 +308,7 @@ static int pick_lanes(double mean_row) {
 // SELL-32-sigma layout of a subset of rows: permutation (padded with -1 to whole slices),
 // slice pointers relative to `base`, and the entry count.
 static void sell_layout(const HostCsr &h, const std::vector<int32_t> &rows, std::vector<int32_t> &perm,
-                        std::vector<int32_t> &ptr, int64_t &total) {
+                        std::vector<int32_t> &ptr, int64_t &total, int64_t SELL_SIGMA) {
   const int64_t n = (int64_t)rows.size();
   const int64_t nsl = (n + SELL_C - 1) / SELL_C;
   perm.assign((size_t)nsl * SELL_C, -1);
@@ -239,7 +360,7 @@ static void sell_fill(const HostCsr &h, const std::vector<int32_t> &perm, const 
 // Build the SELL copy of a pattern.  With n_own_split >= 0 (multi-rank) the rows are split
 // into an interior part (no ghost column) and a boundary part, so that the interior part
 // can run while the halo exchange is in flight.
-static void build_sell(Ctx &c, DevCsr &A, const HostCsr &h, int64_t n_own_split) {
+static void build_sell(Ctx &c, DevCsr &A, const HostCsr &h, int64_t n_own_split, int64_t n_own_cols) {
   std::vector<int32_t> rows_a, rows_b;
   rows_a.reserve(h.nrows);
   for (int64_t i = 0; i < h.nrows; ++i) {
@@ -251,13 +372,32 @@ static void build_sell(Ctx &c, DevCsr &A, const HostCsr &h, int64_t n_own_split)
   }
   std::vector<int32_t> perm_a, ptr_a, perm_b, ptr_b;
   int64_t tot_a = 0, tot_b = 0;
-  sell_layout(h, rows_a, perm_a, ptr_a, tot_a);
-  sell_layout(h, rows_b, perm_b, ptr_b, tot_b);
+  sell_layout(h, rows_a, perm_a, ptr_a, tot_a, c.sell_sigma);
+  sell_layout(h, rows_b, perm_b, ptr_b, tot_b, c.sell_sigma);
   FNP_REQUIRE(tot_a + tot_b < (int64_t)INT32_MAX, FNP_ERR_ARG, "SELL layout exceeds 2^31 entries on one rank");
   std::vector<int32_t> col((size_t)(tot_a + tot_b));
   A.sell_pos.assign((size_t)h.nnz(), 0);
   sell_fill(h, perm_a, ptr_a, 0, col, A.sell_pos);
   sell_fill(h, perm_b, ptr_b, tot_a, col, A.sell_pos);
+  // slices whose entries (padding included) address the first or last node of the owned
+  // vector or of the ghost buffer: the 16-byte gathers of the Kronecker kernel would read
+  // outside, flag them for the scalar loads
+  {
+    const int32_t nown = n_own_cols >= 0 ? (int32_t)n_own_cols : (int32_t)h.ncols;
+    const int32_t edge[4] = {0, nown - 1, nown, (int32_t)h.ncols - 1};
+    auto flag = [&](std::vector<int32_t> &ptr, const std::vector<int32_t> &perm, int64_t off) {
+      for (size_t sl = 0; sl + 1 < ptr.size(); ++sl) {
+        bool hit = false;
+        for (int l = 0; l < SELL_C; ++l)     // first / last row: the epilogue's 16-byte loads
+          hit = hit || perm[sl * SELL_C + l] == 0 || perm[sl * SELL_C + l] == (int32_t)h.nrows - 1;
+        for (int64_t k = off + ptr[sl]; k < off + ptr[sl + 1] && !hit; ++k)
+          hit = col[k] == edge[0] || col[k] == edge[1] || col[k] == edge[2] || col[k] == edge[3];
+        if (hit) ptr[sl] |= SELL_NARROW;
+      }
+    };
+    flag(ptr_a, perm_a, 0);
+    flag(ptr_b, perm_b, tot_a);
+  }
   A.nslices = (int32_t)ptr_a.size() - 1;
   A.nslices_b = (int32_t)ptr_b.size() - 1;
   A.sell_entries = tot_a + tot_b;
@@ -272,7 +412,8 @@ static void build_sell(Ctx &c, DevCsr &A, const HostCsr &h, int64_t n_own_split)
   A.sell = true;
 }
 
-void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag, int64_t n_own_split, int bs) {
+void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag, int64_t n_own_split, int bs,
+                        int64_t n_own_cols) {
   A.tag = tag;
   A.bs = bs;
   A.nrows = (int32_t)h.nrows;
@@ -293,7 +434,7 @@ void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &
   const bool short_rows = A.mean_row < c.sell_max_mean_row && maxrow <= 8.0 * std::max(8.0, A.mean_row) && h.nrows >= 4096;
   const bool use_sell = c.spmv_mode == 2 || (c.spmv_mode == 0 && short_rows);
   if (use_sell) {
-    build_sell(c, A, h, n_own_split);
+    build_sell(c, A, h, n_own_split, n_own_cols);
     A.col.release();
     A.val.release();
   } else {
@@ -348,7 +489,20 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
     auto launch = [&](int nsl, const int32_t *ptr, const int32_t *perm, int64_t off) {
       if (nsl <= 0) return;
       const int grid = (int)(((int64_t)nsl * 32 + threads - 1) / threads);
-      spmv_sell_kernel<BS, Epi><<<grid, threads, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, epi);
+#define FNP_SELL(V) \
+  spmv_sell_kernel<BS, Epi, V><<<grid, threads, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, epi)
+      if (BS == 3) {
+        switch (c.sell_gather & 15) {
+          case 0: FNP_SELL(0); break;
+          case 4: FNP_SELL(4); break;
+          case 7: FNP_SELL(7); break;
+          default: FNP_SELL(15); break;
+        }
+      } else {
+        if (c.sell_gather & 4) FNP_SELL(4);
+        else FNP_SELL(0);
+      }
+#undef FNP_SELL
       FNP_LAUNCH_CHECK(c);
     };
     if (A.halo && A.nslices_b > 0) {

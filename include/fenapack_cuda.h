@@ -100,7 +100,12 @@ int fnp_synchronize(fnp_context *ctx);
  *   pc_amg_eig_ratio, pc_amg_prolongator_truncation, pc_amg_coarse_drop, pc_amg_replicate_size,
  *   pc_amg_lag (velocity block: rebuild the coarse levels at every lag-th refresh only) for the prefixes fieldsplit_u_ and fieldsplit_p_PCD_Ap_
  * "hypre"/"boomeramg"/"gamg" are accepted as aliases of amg (the smoothed-
- * aggregation hierarchy of this library).  Unknown names -> FNP_ERR_OPTION. */
+ * aggregation hierarchy of this library).  Unknown names -> FNP_ERR_OPTION.
+ * Library tuning knobs (prefix fnp_, not PETSc names): fnp_timers, fnp_cuda_graph, fnp_spmv_kernel
+ * auto|csr|sell, fnp_sell_max_mean_row, fnp_sell_sigma (sorting window, before fnp_set_pattern),
+ * fnp_sell_gather (bit mask: 1 16-byte gathers, 2 six CTAs/SM, 4 L2 bulk prefetch, 8 16-byte epilogue
+ * loads; default 15, results are bit-identical for every value), fnp_kronecker, fnp_prune_zeros,
+ * fnp_halo_overlap, fnp_halo_p2p. */
 int fnp_set_option(fnp_context *ctx, const char *name, const char *value);
 
 /* ---- operators -------------------------------------------------------- */

@@ -94,3 +94,41 @@ def test_kronecker_and_general_storage_agree(setup):
     # and the pressures up to their mean
     assert relerr(gu, xu) <= 1e-6
     assert relerr(gp - gp.mean(), xp - xp.mean()) <= 1e-5
+
+
+def test_sell_kernel_variants_bit_identical(setup):
+    """fnp_sell_gather bits (16-byte gathers, 6 CTAs/SM, L2 bulk prefetch, 16-byte epilogue loads)
+    change how the Kronecker SELL kernel loads, never what it computes: identical bits for the
+    SpMV on 16-byte aligned and misaligned vectors, for a PC apply (Chebyshev / axpby epilogues)."""
+    import torch
+    prob, ctx, _, capi = setup
+    g = torch.Generator(device="cuda").manual_seed(5)
+    buf = torch.randn(prob.n_u + prob.n_p + 4, dtype=torch.float64, device="cuda", generator=g)
+    out = torch.empty(prob.n_u + prob.n_p + 4, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ref = {}
+    try:
+        for variant in (0, 4, 7, 15):
+            ctx.set_option("fnp_sell_gather", variant)
+            for shift in (0, 1):                              # x, y at 0 and 8 bytes past a 16-byte boundary
+                x, y = buf[shift:shift + prob.n_u], out[shift:shift + prob.n_u]
+                out.zero_()
+                torch.cuda.synchronize()
+                ctx.spmv_device(capi.MAT_A00, x.data_ptr(), y.data_ptr())
+                ctx.synchronize()
+                got = y.clone()
+                if variant == 0 and shift == 0:
+                    A = prob.scipy("A00")
+                    assert relerr(got.cpu().numpy(), A @ x.cpu().numpy()) <= 1e-12
+                ref.setdefault(("spmv", shift), got)
+                assert torch.equal(got, ref[("spmv", shift)]), (variant, shift)
+                assert float(out[prob.n_u + shift:].abs().max()) == 0.0       # nothing written past y
+                xu, xp = buf[shift:shift + prob.n_u], buf[prob.n_u + 2:prob.n_u + 2 + prob.n_p]
+                zu, zp = out[shift:shift + prob.n_u], out[prob.n_u + 2:prob.n_u + 2 + prob.n_p]
+                ctx.pc_apply_device(xu.data_ptr(), xp.data_ptr(), zu.data_ptr(), zp.data_ptr())
+                ctx.synchronize()
+                got = torch.cat([zu, zp]).clone()
+                ref.setdefault(("pc", shift), got)
+                assert torch.equal(got, ref[("pc", shift)]), (variant, shift)
+    finally:
+        ctx.set_option("fnp_sell_gather", 15)
