@@ -6,17 +6,30 @@ be imported only by ``tests/``, ``__graft_entry__.smoke()`` and the
 the checker or as the CPU arm that is timed next to the GPU, never as the thing
 shipped.
 
-PARITY UNPINNED.  The reference (blechta/fenapack, /root/reference) only *wires*
-third-party solvers together (PETSc KSP/PC/Mat/Vec, hypre BoomerAMG, MUMPS,
-DOLFIN assembly); none of them is vendored, none is installed in this image, no
-version is pinned (README.rst:26 names only "FEniCS 2019.2.0.dev0"), and the
-reference's own tests assert nothing on this path except "the solve converged"
-(test/bench/test_pcd_scaling.py:223).  There are therefore no golden vectors to
-pin this restatement against; it is pinned instead by the self-consistency
-properties listed in SURVEY.md section 8c (exact-Schur two-iteration
-convergence, Chebyshev polynomial optimality, convergence of all 16 scenario
-combinations of the reference bench, iteration counts in the neighbourhood of
-the un-asserted table in demo/unsteady-navier-stokes-pcd/documentation.rst:137).
+PARITY: PINNED FOR THE REFERENCE-OWNED PART, UNPINNED FOR THE PETSc-OWNED PART.
+The reference (blechta/fenapack, /root/reference) *wires* third-party solvers
+together (PETSc KSP/PC/Mat/Vec, hypre BoomerAMG, MUMPS, DOLFIN assembly); none of
+them is vendored, none is installed in this image, no version is pinned
+(README.rst:26 names only "FEniCS 2019.2.0.dev0"), and the reference's own tests
+assert nothing on this path except "the solve converged"
+(test/bench/test_pcd_scaling.py:223): it holds no golden vectors.
+  * pinned: what the reference's own Python computes -- the four Schur-complement
+    applies PCDPC_BRM1/2 and PCDRPC_BRM1/2 (order of operations, signs, where the
+    subfield BC is applied), PCDInterface's operator extraction / refresh protocol
+    and its Rp = B diag(Mu)^-1 B^T.  tests/golden/make_reference_golden.py executes
+    fenapack/preconditioners.py and field_split_backend.py UNMODIFIED in this
+    container (numpy/scipy stand-ins for the petsc4py objects they call, Cholesky
+    inner solves = the reference's default) and commits the outputs as
+    tests/golden/ref_pcd_apply.npz; tests/test_reference_golden.py holds the oracle
+    to them at 1e-11 and the CUDA library at 1e-8.
+  * unpinned: the algorithms that live inside PETSc / hypre (KSPGMRES, PCFIELDSPLIT
+    Schur/upper, KSPCHEBYSHEV, KSPRICHARDSON; BoomerAMG is replaced by SA-AMG on both
+    sides).  They are restated from the published algorithms ("recalled" details:
+    SURVEY.md appendix B) and held by the self-consistency properties of SURVEY.md
+    section 8c (exact-Schur two-iteration convergence, Chebyshev polynomial
+    optimality, convergence of all 16 scenario combinations of the reference bench,
+    iteration counts in the neighbourhood of the un-asserted table in
+    demo/unsteady-navier-stokes-pcd/documentation.rst:137).
 
 Modules
 -------

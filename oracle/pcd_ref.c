@@ -1,6 +1,7 @@
 /* C / OpenMP restatement of the PCD-preconditioned FGMRES path -- TEST
  * INFRASTRUCTURE and the CPU arm timed by bench.py (cpu_baseline, --impl
- * reference).  PARITY UNPINNED (see oracle/__init__.py): the reference only wires
+ * reference).  PARITY UNPINNED for the PETSc-owned algorithms (see oracle/__init__.py; the
+ * Schur applies are pinned through the numpy restatement): the reference only wires
  * PETSc / hypre together; this file restates the same algorithm chain as
  * oracle/petsc_algos.py + oracle/amg.py, function for function, so that it can be
  * (a) checked against the numpy restatement and (b) timed on all host cores,

@@ -1,8 +1,11 @@
 """Restatement (numpy, float64) of the PETSc algorithm chain FENaPack selects --
-TEST INFRASTRUCTURE.  PARITY UNPINNED: PETSc is not vendored in /root/reference,
-not installed here, and no release is pinned; the recurrences below are restated
-from the published algorithms and are marked "recalled" where the PETSc source
-decides a detail.
+TEST INFRASTRUCTURE.  PARITY UNPINNED for the PETSc algorithms: PETSc is not vendored
+in /root/reference, not installed here, and no release is pinned; the recurrences
+below are restated from the published algorithms and are marked "recalled" where the
+PETSc source decides a detail.  PINNED for the functions that
+restate the reference's own Python (brm1/brm2/pcdr_* apply, build_rp, apply_bcs):
+tests/test_reference_golden.py checks them against outputs of the reference's code
+run in this container (tests/golden/make_reference_golden.py).
 
   reference call site                                   restated here
   fenapack/preconditioners.py:124-135  (PCDPC_BRM1.apply)   brm1_apply

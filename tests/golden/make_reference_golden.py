@@ -1,0 +1,106 @@
+"""Golden vectors produced by the REFERENCE'S OWN code for the part of the hot path it owns.
+
+/root/reference/fenapack/preconditioners.py and field_split_backend.py are executed here, unmodified,
+on top of the numpy/scipy stand-ins of tests/golden/refstubs.py (petsc4py and DOLFIN are not
+installed; see that file for what is real and what is a stand-in).  The run goes through the
+python-PC protocol exactly as PETSc drives it -- create(pc), init_pcd(PCDInterface), setUp(pc),
+apply(pc, x, y) -- in the reference's DEFAULT configuration (PREONLY + Cholesky inner solves), for
+PCDPC_BRM1, PCDPC_BRM2, PCDRPC_BRM1, PCDRPC_BRM2, with shallow and deep sub-matrices.
+
+Inputs: backward-facing step, level 2, nu = 0.02, Oseen wind = the Stokes solution; PCDR: dt = 0.2.
+The matrices come from oracle/fem.py (the reference assembles them with DOLFIN), embedded in the
+mixed space with the DOLFIN-like interleaved numbering of oracle.problems.interleaved_index_sets.
+
+Output: tests/golden/ref_pcd_apply.npz -- x, the reference's y per class, the Rp matrix the
+reference builds, and the BC index list its SubfieldBC mapping produces.  tests/test_reference_golden.py
+checks the oracle against these (CPU) and the CUDA library against them (GPU).  Needs /root/reference:
+    python tests/golden/make_reference_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+import refstubs as rs  # noqa: E402
+from oracle import fem, petsc_algos as pa, problems  # noqa: E402
+
+LEVEL, NU, DT = 2, 0.02, 0.2
+
+
+def build_problem(variant, pcdr):
+    p0, _ = problems.backward_facing_step(LEVEL, nu=NU, variant=variant)
+    x = pa.direct_solver(p0.system_matrix())(p0.rhs())
+    wind = x[:p0.n_u].reshape(-1, 2)
+    idt = 1.0 / DT if pcdr else 0.0
+    prob, space = problems.backward_facing_step(LEVEL, nu=NU, variant=variant, wind=wind, idt=idt, pcdr=pcdr)
+    return prob, space, idt
+
+
+def reference_apply(pcmod, fsb, cls_name, prob, space, idt, x, deep):
+    n = prob.n_u + prob.n_p
+    is_u, is_p = prob.is_u, prob.is_p
+    blocks = {"ap": prob.Ap, "mp": prob.Mp, "kp": prob.Kp}
+    if idt:
+        asm = fem.Assembler(space)
+        blocks["mu"] = asm.velocity_block(asm.p2_scalar(mass_coeff=idt))
+    bc_mixed = {int(is_p[i]): float(v) for i, v in zip(prob.bc_idx, prob.bc_val)}
+    # a velocity Dirichlet dof as well: SubfieldBC must ignore dofs outside the index set
+    bc_mixed[int(is_u[0])] = 7.0
+    assembler = rs.PCDAssembler(n, is_u, is_p, blocks, bc_mixed)
+    # monolithic system matrix (PCDR takes Bt from it: gp is a phantom form)
+    M = sp.bmat([[prob.A00, prob.A01], [prob.A10, None]], format="coo")
+    perm = np.concatenate([is_u, is_p])
+    A = rs.Mat(sp.csr_matrix((M.data, (perm[M.row], perm[M.col])), shape=(n, n)))
+    interface = fsb.PCDInterface(assembler, A, rs.IS(is_u), rs.IS(is_p), deep_submats=deep)
+    pc = rs._PCHandle("fieldsplit_p_")
+    ctx = getattr(pcmod, cls_name)()
+    ctx.create(pc)
+    ctx.setFromOptions(pc)
+    ctx.init_pcd(interface)
+    ctx.setUp(pc)
+    xv, yv = rs.Vec(x), rs.Vec(np.full_like(x, np.nan))
+    ctx.apply(pc, xv, yv)
+    assert np.array_equal(xv.array, x), "apply must not modify x"
+    # second PCSetUp + apply (what a Newton step does): Ap/Mp are not re-assembled, Kp is
+    calls_before = list(assembler.calls)
+    ctx.setUp(pc)
+    again = [c for c in assembler.calls[len(calls_before):]]
+    y2 = rs.Vec(np.zeros_like(x))
+    ctx.apply(pc, xv, y2)
+    assert np.array_equal(y2.array, yv.array)
+    extra = {"refresh_assembles": np.array(again)}
+    extra["prefixes"] = np.array([ctx.ksp_Ap.getOptionsPrefix(), ctx.ksp_Mp.getOptionsPrefix(), ctx.mat_Kp.getOptionsPrefix()])
+    sub = interface._subbcs[0]
+    extra["bc_idx"], extra["bc_val"] = sub.idx, sub.val
+    if hasattr(ctx, "ksp_Rp"):
+        Rp = ctx.ksp_Rp.getOperators()[0].csr.tocsr()
+        Rp.sort_indices()
+        extra["Rp_indptr"], extra["Rp_indices"], extra["Rp_data"] = Rp.indptr, Rp.indices, Rp.data
+    return yv.array.copy(), extra
+
+
+def main():
+    pcmod, fsb = rs.load_reference_modules()
+    out = {"level": np.array([LEVEL]), "nu": np.array([NU]), "dt": np.array([DT])}
+    rng = np.random.default_rng(7)
+    for cls_name, variant, pcdr in (("PCDPC_BRM1", "BRM1", False), ("PCDPC_BRM2", "BRM2", False),
+                                    ("PCDRPC_BRM1", "BRM1", True), ("PCDRPC_BRM2", "BRM2", True)):
+        prob, space, idt = build_problem(variant, pcdr)
+        x = rng.standard_normal(prob.n_p)
+        y_shallow, extra = reference_apply(pcmod, fsb, cls_name, prob, space, idt, x, deep=False)
+        y_deep, _ = reference_apply(pcmod, fsb, cls_name, prob, space, idt, x, deep=True)
+        assert np.array_equal(y_shallow, y_deep)
+        out[f"{cls_name}_x"], out[f"{cls_name}_y"] = x, y_shallow
+        for k, v in extra.items():
+            out[f"{cls_name}_{k}"] = v
+        print(cls_name, "n_p", prob.n_p, "|y|", np.linalg.norm(y_shallow), "refresh assembles", list(extra["refresh_assembles"]))
+    np.savez_compressed(os.path.join(HERE, "ref_pcd_apply.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,7 @@
 """CPU tests of the oracle (the checker itself).  The reference pins no numbers on
-this path (PARITY UNPINNED, oracle/__init__.py), so the restatement is pinned by the
-self-consistency properties of SURVEY.md section 8c and by the committed fixtures."""
+this path (oracle/__init__.py), so the PETSc-owned part of the restatement is pinned by the
+self-consistency properties of SURVEY.md section 8c and by the committed fixtures; the part the
+reference's own Python owns is pinned against its code in tests/test_reference_golden.py."""
 import os
 
 import numpy as np
