@@ -84,7 +84,73 @@ def reference_apply(pcmod, fsb, cls_name, prob, space, idt, x, deep):
     return yv.array.copy(), extra
 
 
+def assembler_inputs():
+    """A small mixed space (26 velocity + 14 pressure dofs, interleaved) with random sparse
+    'forms' as host callables; velocity BCs with non-zero values, PCD BCs on two pressure dofs."""
+    rng = np.random.default_rng(11)
+    n = 40
+    is_p = np.arange(2, n, 3)[:14]
+    is_u = np.setdiff1d(np.arange(n), is_p)
+
+    def rand(seed, rows, cols, density=0.3):
+        r = np.random.default_rng(seed)
+        M = sp.random(n, n, density=density, random_state=r, format="coo")
+        keep = np.isin(M.row, rows) & np.isin(M.col, cols)
+        M = sp.coo_matrix((M.data[keep], (M.row[keep], M.col[keep])), shape=(n, n)).tocsr()
+        return (M + sp.diags(np.isin(np.arange(n), np.intersect1d(rows, cols)).astype(float))).tocsr()
+    mats = {"a": rand(1, np.arange(n), np.arange(n)), "a_pc": rand(2, np.arange(n), np.arange(n)),
+            "mp": rand(3, is_p, is_p), "mu": rand(4, is_u, is_u), "ap": rand(5, is_p, is_p),
+            "fp": rand(6, is_p, is_p), "kp": rand(7, is_p, is_p), "gp": rand(8, is_u, is_p)}
+    Lvec = rng.standard_normal(n)
+    forms = {k: (lambda M=M: M.copy()) for k, M in mats.items()}
+    forms["L"] = lambda: Lvec.copy()
+    bcs = [rs.HostBC(is_u[[0, 3, 7]], [1.5, -2.0, 0.25]), rs.HostBC(is_u[[10]], [4.0])]
+    bcs_pcd = [rs.HostBC(is_p[[1, 5]], [0.0, 0.0])]
+    x_newton = rng.standard_normal(n)
+    return n, forms, bcs, bcs_pcd, x_newton
+
+
+def run_assembler(cls, n, forms, bcs, bcs_pcd, x_newton):
+    """Drive a PCDAssembler class (the reference's or the drop-in) through every public method."""
+    asm = cls(forms["a"], forms["L"], bcs, forms["a_pc"], mp=forms["mp"], mu=forms["mu"], ap=forms["ap"],
+              fp=forms["fp"], kp=forms["kp"], gp=forms["gp"], bcs_pcd=bcs_pcd)
+    out = {}
+    for name in ("system_matrix", "pc_matrix", "ap", "mp", "mu", "fp", "kp", "gp"):
+        T = rs.HostTensor()
+        getattr(asm, name)(T)
+        out[name] = T.csr.toarray()
+    b = rs.HostTensor(n)
+    asm.rhs_vector(b)
+    out["rhs"] = b.array.copy()
+    xv = rs.HostTensor(n)
+    xv.array[:] = x_newton
+    b2 = rs.HostTensor(n)
+    asm.rhs_vector(b2, xv)
+    out["rhs_newton"] = b2.array.copy()
+    keys = ("ap", "mp", "mu", "fp", "kp", "gp")
+    out["flags_constant"] = np.array([asm.get_pcd_form(k).is_constant() for k in keys])
+    out["flags_phantom"] = np.array([asm.get_pcd_form(k).is_phantom() for k in keys])
+
+    def raises(f):
+        try:
+            f()
+        except AttributeError:
+            return True
+        return False
+    out["unknown_form_raises"] = np.array([raises(lambda: asm.get_pcd_form("nope"))])
+    bare = cls(forms["a"], forms["L"], bcs)
+    out["missing_form_is_none"] = np.array([bare.get_dolfin_form("fp") is None])
+    out["default_pcd_bcs_empty"] = np.array([not raises(bare.pcd_bcs) and len(bare.pcd_bcs()) == 0])
+    out["none_pcd_bcs_raises"] = np.array([raises(cls(forms["a"], forms["L"], bcs, bcs_pcd=None).pcd_bcs)])
+    out["pc_matrix_without_a_pc_is_noop"] = np.array([bare.pc_matrix(rs.HostTensor()) is None])
+    return out
+
+
 def main():
+    asm_mod = rs.load_reference_assembling()
+    ref = run_assembler(asm_mod.PCDAssembler, *assembler_inputs())
+    np.savez_compressed(os.path.join(HERE, "ref_assembler.npz"), **ref)
+    print("PCDAssembler protocol:", {k: v.tolist() for k, v in ref.items() if v.size <= 6})
     pcmod, fsb = rs.load_reference_modules()
     out = {"level": np.array([LEVEL]), "nu": np.array([NU]), "dt": np.array([DT])}
     rng = np.random.default_rng(7)

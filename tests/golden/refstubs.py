@@ -386,3 +386,103 @@ def load_reference_modules():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+# ------------------------------------------------------------------ fenapack/assembling.py
+class HostTensor:
+    """Matrix or vector handed to the assembler (the role of dolfin.PETScMatrix / PETScVector)."""
+
+    def __init__(self, n=None):
+        self.csr = None
+        self.array = None if n is None else np.zeros(n)
+
+    def set_csr(self, csr):
+        self.csr = sp.csr_matrix(csr)
+
+
+class HostBC:
+    """Dirichlet condition on mixed-space dofs; serves the reference (``apply``) and the
+    drop-in (``dofs`` / ``values``)."""
+
+    def __init__(self, dofs, values):
+        self._dofs = np.asarray(dofs, dtype=np.int64)
+        self._vals = np.asarray(values, dtype=np.float64)
+
+    def dofs(self):
+        return self._dofs
+
+    def values(self):
+        return self._vals
+
+    def get_boundary_values(self):
+        return {int(d): float(v) for d, v in zip(self._dofs, self._vals)}
+
+    def apply(self, tensor):
+        """DirichletBC.apply(A): BC rows zeroed, unit diagonal."""
+        A = sp.lil_matrix(tensor.csr)
+        for d in self._dofs:
+            A.rows[d], A.data[d] = [int(d)], [1.0]
+        tensor.set_csr(A.tocsr())
+
+
+class _SystemAssembler:
+    """dolfin.SystemAssembler semantics on host callables: symmetric elimination of the BC dofs,
+    rhs lifted; ``assemble(b, x)`` is the Newton variant (BC value g - x)."""
+
+    def __init__(self, a, L, bcs):
+        self.a, self.L, self.bcs = a, L, list(bcs) if bcs is not None else []
+
+    def assemble(self, *tensors):
+        dofs = np.concatenate([bc.dofs() for bc in self.bcs]) if self.bcs else np.zeros(0, dtype=np.int64)
+        g = np.concatenate([bc.values() for bc in self.bcs]) if self.bcs else np.zeros(0)
+        A = sp.csr_matrix(self.a())
+        mats = [t for t in tensors if t.array is None]
+        vecs = [t for t in tensors if t.array is not None]
+        if vecs:
+            b = vecs[0]
+            if len(vecs) == 2:
+                g = g - vecs[1].array[dofs]
+            lift = np.zeros(A.shape[1])
+            lift[dofs] = g
+            rhs = np.array(self.L(), dtype=np.float64) - A @ lift
+            rhs[dofs] = g
+            b.array[:] = rhs
+        if mats:
+            D = sp.lil_matrix(A)
+            mask = np.zeros(A.shape[0], dtype=bool)
+            mask[dofs] = True
+            C = sp.coo_matrix(A)
+            keep = ~(mask[C.row] | mask[C.col])
+            E = sp.coo_matrix((C.data[keep], (C.row[keep], C.col[keep])), shape=A.shape).tolil()
+            for d in dofs:
+                E[d, d] = 1.0
+            del D
+            mats[0].set_csr(E.tocsr())
+
+
+def _assemble(form, tensor=None):
+    tensor.set_csr(form())
+    return tensor
+
+
+def load_reference_assembling():
+    """The reference's fenapack/assembling.py with dolfin.SystemAssembler / dolfin.assemble replaced
+    by the host stand-ins above."""
+    saved = {k: sys.modules.get(k) for k in ("dolfin", "fenapack", "fenapack.assembling")}
+    dolfin = types.ModuleType("dolfin")
+    dolfin.SystemAssembler, dolfin.assemble = _SystemAssembler, _assemble
+    pkg = types.ModuleType("fenapack")
+    pkg.__path__ = []
+    sys.modules.update({"dolfin": dolfin, "fenapack": pkg})
+    try:
+        spec = importlib.util.spec_from_file_location("fenapack.assembling", f"{REF}/assembling.py")
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["fenapack.assembling"] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

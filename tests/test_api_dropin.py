@@ -60,12 +60,14 @@ def test_pcd_form_flags_and_assembler_defaults():
     assert asm.get_pcd_form("ap").is_constant() and asm.get_pcd_form("mp").is_constant()
     assert not asm.get_pcd_form("kp").is_constant()
     assert asm.get_pcd_form("gp").phantom and asm.get_pcd_form("gp").is_phantom()
+    assert asm.get_dolfin_form("fp") is None             # reference assembling.py:117-119
     with pytest.raises(AttributeError):
-        asm.get_dolfin_form("fp")
+        asm.fp(Mat())                                    # ... assembling a missing form is the error
     with pytest.raises(AttributeError):
         asm.get_pcd_form("nope")
+    assert fp.PCDAssembler(m.a, m.L, [], function_space=m.W).pcd_bcs() == []   # default, assembling.py:184-189
     with pytest.raises(AttributeError):
-        fp.PCDAssembler(m.a, m.L, [], function_space=m.W).pcd_bcs()
+        fp.PCDAssembler(m.a, m.L, [], bcs_pcd=None, function_space=m.W).pcd_bcs()
     Ap = Mat()
     asm.ap(Ap)
     d = Ap.csr.diagonal()
