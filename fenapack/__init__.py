@@ -5,4 +5,4 @@ the public names of the reference package (fenapack/__init__.py:35-40) must be
 importable as ``fenapack.<name>``.  Everything lives in ``fenapack_b200``."""
 from fenapack_b200 import (PCDKSP, PCDAssembler, PCDForm, PCDKrylovSolver,  # noqa: F401
                            PCDNewtonSolver, PCDNonlinearProblem, PCDPC_BRM1, PCDPC_BRM2,
-                           PCDRPC_BRM1, PCDRPC_BRM2, __version__)
+                           PCDRPC_BRM1, PCDRPC_BRM2, StabilizationParameterSD, __version__)

@@ -8,6 +8,7 @@ P2/P1 Oseen / Navier-Stokes system.
 ``field_split_backend`` PCDInterface                          (reference: fenapack/field_split_backend.py)
 ``assembling``      PCDAssembler / PCDForm                    (reference: fenapack/assembling.py)
 ``nonlinear_solvers`` PCDNewtonSolver / PCDNonlinearProblem   (reference: fenapack/nonlinear_solvers.py)
+``stabilization``   StabilizationParameterSD (host helper)    (reference: fenapack/stabilization.py)
 
 The CUDA library is mandatory; nothing here falls back to the CPU.
 """
@@ -17,3 +18,4 @@ from .assembling import PCDAssembler, PCDForm  # noqa: E402,F401
 from .field_split import PCDKSP, PCDKrylovSolver  # noqa: E402,F401
 from .nonlinear_solvers import PCDNewtonSolver, PCDNonlinearProblem  # noqa: E402,F401
 from .preconditioners import PCDPC_BRM1, PCDPC_BRM2, PCDRPC_BRM1, PCDRPC_BRM2  # noqa: E402,F401
+from .stabilization import StabilizationParameterSD  # noqa: E402,F401

@@ -50,7 +50,7 @@ def test_allow_only_one_call_and_public_names():
         a.f()
     assert A().f() == 1
     for name in ("PCDKSP", "PCDKrylovSolver", "PCDAssembler", "PCDForm", "PCDNewtonSolver", "PCDNonlinearProblem",
-                 "PCDPC_BRM1", "PCDPC_BRM2", "PCDRPC_BRM1", "PCDRPC_BRM2"):
+                 "PCDPC_BRM1", "PCDPC_BRM2", "PCDRPC_BRM1", "PCDRPC_BRM2", "StabilizationParameterSD"):
         assert hasattr(fp, name)
 
 

@@ -177,3 +177,25 @@ def test_golden_fixture_regression():
         assert np.linalg.norm(yp - g[f"{variant}_direct_yp"]) <= 1e-9 * np.linalg.norm(yp)
         ch = pa.chebyshev_jacobi(prob.Mp, 1.0 / prob.Mp.diagonal(), xp, 0.5, 2.0, 5)
         assert np.linalg.norm(ch - g[f"{variant}_cheb"]) <= 1e-13 * np.linalg.norm(ch)
+
+
+def test_streamline_diffusion_parameter_matches_oracle_assembler():
+    """fenapack_b200.StabilizationParameterSD (host helper, reference stabilization.py:64-67)
+    against the oracle assembler's per-cell parameter on the BFS mesh."""
+    from fenapack_b200 import StabilizationParameterSD
+    from oracle import fem
+    p0, space = problems.backward_facing_step(2)
+    x = pa.direct_solver(p0.system_matrix())(p0.rhs())
+    wind = x[:p0.n_u].reshape(-1, 2)
+    asm = fem.Assembler(space)
+    nu = 0.002                                   # low viscosity: part of the cells has PE > 1
+    delta = asm.sd_parameter(wind, nu)
+    lam_mid = np.full((1, 3), 1.0 / 3.0)
+    phi_mid, _ = fem.p2_basis(lam_mid, space.pairs)
+    wmid = np.einsum("l,cld->cd", phi_mid[0], wind[space.cell_nodes])
+    sd = StabilizationParameterSD(lambda cells: wmid, nu)
+    got = sd.eval_cells(space.cell_diameter())
+    assert 0 < np.count_nonzero(got) < got.size
+    assert np.array_equal(got, delta)
+    # density scales the Peclet number only
+    assert np.count_nonzero(StabilizationParameterSD(wmid, nu, 0.5).eval_cells(space.cell_diameter())) <= np.count_nonzero(got)
