@@ -213,6 +213,8 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
     else throw Error(FNP_ERR_OPTION, "option fnp_spmv_kernel: auto | csr | sell (takes effect at fnp_set_pattern)");
   } else if (name == "fnp_halo_p2p") {
     c.p2p = parse_int(name, v);
+  } else if (name == "fnp_reorder_nodes") {
+    c.reorder = std::max(0, (int)parse_int(name, v)) / 6 * 6;   // windows hold whole nodes for 2 and 3 components
   } else if (name == "fnp_sell_gather") {
     c.sell_gather = (int)parse_int(name, v);
     c.drop_graph();
@@ -417,6 +419,80 @@ static void set_values(Ctx &c, int which, const double *values) {
   c.dirty[which] = true;
 }
 
+// opt-in internal numbering of the velocity dofs (Ctx::reorder) ------------------
+static bool u_rows(int which) { return which == FNP_MAT_A00 || which == FNP_MAT_P00 || which == FNP_MAT_A01; }
+static bool u_cols(int which) { return which == FNP_MAT_A00 || which == FNP_MAT_P00 || which == FNP_MAT_A10; }
+
+// Permuted copy of a user pattern: internal row i = user row u_perm[i] (velocity rows), columns
+// mapped through u_inv (velocity columns); c.rmap[which] maps internal entries to user entries.
+// FNP_MAT_A00 defines the permutation: dofs sorted by row length inside windows of c.reorder dofs
+// (stable, so the components of a node -- equal row lengths, adjacent -- stay interleaved).
+static void reorder_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t *colidx, std::vector<int32_t> &rp,
+                            std::vector<int32_t> &ci) {
+  c.rmap[which].clear();
+  if (!u_rows(which) && !u_cols(which)) return;
+  FNP_REQUIRE(c.nranks == 1, FNP_ERR_OPTION, "fnp_reorder_nodes is available on single-rank contexts only");
+  if (which == FNP_MAT_A00) {
+    FNP_REQUIRE(!c.have_pattern[FNP_MAT_A01] && !c.have_pattern[FNP_MAT_A10] && !c.have_pattern[FNP_MAT_P00] && c.mu_diag.empty() &&
+                    !c.have_is,
+                FNP_ERR_STATE, "with fnp_reorder_nodes, FNP_MAT_A00 must be set before the other velocity data");
+    const int64_t n = c.n_u;
+    c.u_perm.resize(n);
+    std::iota(c.u_perm.begin(), c.u_perm.end(), (int64_t)0);
+    for (int64_t w0 = 0; w0 < n; w0 += c.reorder) {
+      const int64_t w1 = std::min<int64_t>(n, w0 + c.reorder);
+      std::stable_sort(c.u_perm.begin() + w0, c.u_perm.begin() + w1, [&](int64_t a, int64_t b) {
+        return rowptr[a + 1] - rowptr[a] > rowptr[b + 1] - rowptr[b];
+      });
+    }
+    c.u_inv.resize(n);
+    for (int64_t i = 0; i < n; ++i) c.u_inv[c.u_perm[i]] = i;
+    c.d_u_perm.upload(c.u_perm.data(), (size_t)n, c.stream);
+    FNP_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  FNP_REQUIRE(c.reordered(), FNP_ERR_STATE, "with fnp_reorder_nodes, FNP_MAT_A00 must be set before the other velocity data");
+  int64_t nrows, ncols;
+  op_shape(c, which, nrows, ncols);
+  FNP_REQUIRE(rowptr[0] == 0, FNP_ERR_ARG, "rowptr[0] must be 0");
+  for (int64_t i = 0; i < nrows; ++i) FNP_REQUIRE(rowptr[i + 1] >= rowptr[i], FNP_ERR_ARG, "rowptr not monotone");
+  const int64_t nnz = rowptr[nrows];
+  rp.assign(nrows + 1, 0);
+  ci.resize(nnz);
+  std::vector<int64_t> &map = c.rmap[which];
+  map.resize(nnz);
+  const bool pr = u_rows(which), pc = u_cols(which);
+  for (int64_t i = 0; i < nrows; ++i) {
+    const int64_t r = pr ? c.u_perm[i] : i;
+    rp[i + 1] = rp[i] + (rowptr[r + 1] - rowptr[r]);
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nrows; ++i) {
+    const int64_t r = pr ? c.u_perm[i] : i;
+    for (int32_t k = rowptr[r], q = rp[i]; k < rowptr[r + 1]; ++k, ++q) {
+      int32_t col = colidx[k];
+      if (pc && col >= 0 && col < ncols) col = (int32_t)c.u_inv[col];   // out-of-range ids are reported by set_pattern
+      ci[q] = col;
+      map[q] = k;
+    }
+  }
+}
+
+// user velocity vector (device) -> internal numbering, and back
+static const double *u_to_internal(Ctx &c, const double *user, DevBuf<double> &buf) {
+  if (!c.reordered()) return user;
+  buf.ensure((size_t)c.n_u);
+  vec_gather(c, c.n_u, c.d_u_perm.p, user, buf.p);
+  return buf.p;
+}
+static double *u_internal_out(Ctx &c, double *user) {
+  if (!c.reordered()) return user;
+  c.ro_out.ensure((size_t)c.n_u);
+  return c.ro_out.p;
+}
+static void u_to_user(Ctx &c, const double *internal, double *user) {
+  if (c.reordered()) vec_scatter(c, c.n_u, c.d_u_perm.p, internal, user);
+}
+
 // staging of host-pointer calls ---------------------------------------------
 struct Staged {
   Ctx &c;
@@ -584,6 +660,16 @@ int fnp_set_pattern(fnp_context *ctx, int which, const int32_t *rowptr, const in
   FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must precede fnp_set_pattern");
   FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT, FNP_ERR_ARG, "bad operator id");
   FNP_REQUIRE(rowptr != nullptr, FNP_ERR_ARG, "null pattern");
+  std::vector<int32_t> re_rp, re_ci;
+  if (c.reorder > 0) {
+    reorder_pattern(c, which, rowptr, colidx, re_rp, re_ci);
+    if (!re_rp.empty()) {
+      rowptr = re_rp.data();
+      colidx = re_ci.data();
+    }
+  } else {
+    c.rmap[which].clear();
+  }
   c.user_rowptr[which].clear();
   c.user_col[which].clear();
   c.pattern_pending[which] = false;
@@ -613,6 +699,15 @@ int fnp_set_values(fnp_context *ctx, int which, const double *values) {
   CTX(ctx);
   FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT, FNP_ERR_ARG, "bad operator id");
   FNP_REQUIRE(c.have_pattern[which], FNP_ERR_STATE, "fnp_set_values before fnp_set_pattern");
+  std::vector<double> re_vals;
+  if (!c.rmap[which].empty()) {
+    FNP_REQUIRE(values != nullptr, FNP_ERR_ARG, "null values");
+    const std::vector<int64_t> &map = c.rmap[which];
+    re_vals.resize(map.size());
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)map.size(); ++k) re_vals[k] = values[map[k]];
+    values = re_vals.data();
+  }
   const bool pruning = !c.user_rowptr[which].empty();
   if (pruning) {
     FNP_REQUIRE(values != nullptr, FNP_ERR_ARG, "null values");
@@ -674,6 +769,10 @@ int fnp_set_mu_diag(fnp_context *ctx, const double *diag_local) {
   FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must precede fnp_set_mu_diag");
   FNP_REQUIRE(diag_local != nullptr || c.n_u == 0, FNP_ERR_ARG, "null diagonal");
   c.mu_diag.assign(diag_local, diag_local + c.n_u);
+  if (c.reorder > 0) {
+    FNP_REQUIRE(c.reordered(), FNP_ERR_STATE, "with fnp_reorder_nodes, FNP_MAT_A00 must be set before the other velocity data");
+    for (int64_t i = 0; i < c.n_u; ++i) c.mu_diag[i] = diag_local[c.u_perm[i]];
+  }
   c.mu_dirty = true;
   FNP_API_END
 }
@@ -708,6 +807,13 @@ int fnp_set_index_sets(fnp_context *ctx, const int64_t *is_u_local, const int64_
   check(is_p_local, c.n_p);
   c.is_u.upload(is_u_local, (size_t)c.n_u, c.stream);
   c.is_p.upload(is_p_local, (size_t)c.n_p, c.stream);
+  if (c.reorder > 0) {
+    // internal velocity dof i sits at monolithic position is_u[u_perm[i]]
+    FNP_REQUIRE(c.reordered(), FNP_ERR_STATE, "with fnp_reorder_nodes, FNP_MAT_A00 must be set before the other velocity data");
+    std::vector<int64_t> re((size_t)c.n_u);
+    for (int64_t i = 0; i < c.n_u; ++i) re[(size_t)i] = is_u_local[c.u_perm[i]];
+    c.d_is_u_re.upload(re.data(), re.size(), c.stream);
+  }
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   c.have_is = true;
   FNP_API_END
@@ -729,7 +835,11 @@ int fnp_spmv(fnp_context *ctx, int which, const double *x, double *y, int on_dev
   Staged s(c, on_device != 0);
   const double *dx = s.in(x, A.vec_cols());
   double *dy = s.out(y, A.vec_rows());
-  spmv_store(c, A, dx, dy);
+  const bool rx = c.reordered() && which != FNP_MAT_RP && u_cols(which), ry = c.reordered() && which != FNP_MAT_RP && u_rows(which);
+  const double *ix = rx ? u_to_internal(c, dx, c.ro_in) : dx;
+  double *iy = ry ? u_internal_out(c, dy) : dy;
+  spmv_store(c, A, ix, iy);
+  if (ry) u_to_user(c, iy, dy);
   s.finish();
   FNP_API_END
 }
@@ -776,7 +886,9 @@ int fnp_u_solve(fnp_context *ctx, const double *b, double *x, int on_device) {
   Staged s(c, on_device != 0);
   const double *db = s.in(b, c.n_u);
   double *dx = s.out(x, c.n_u);
-  u_solve(c, db, dx);
+  double *ix = u_internal_out(c, dx);
+  u_solve(c, u_to_internal(c, db, c.ro_in), ix);
+  u_to_user(c, ix, dx);
   s.finish();
   FNP_API_END
 }
@@ -803,7 +915,9 @@ int fnp_pc_apply(fnp_context *ctx, const double *x_u, const double *x_p, double 
   const double *dxp = s.in(x_p, c.n_p);
   double *dyu = s.out(y_u, c.n_u);
   double *dyp = s.out(y_p, c.n_p);
-  pc_apply(c, dxu, dxp, dyu, dyp);
+  double *iyu = u_internal_out(c, dyu);
+  pc_apply(c, u_to_internal(c, dxu, c.ro_in), dxp, iyu, dyp);
+  u_to_user(c, iyu, dyu);
   s.finish();
   check_p2p(c);
   FNP_API_END
@@ -822,12 +936,24 @@ int fnp_solve(fnp_context *ctx, const double *b_u, const double *b_p, double *x_
   bs.ensure((size_t)n);
   const cudaMemcpyKind in_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const cudaMemcpyKind out_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  FNP_CUDA(cudaMemcpyAsync(bs.p, b_u, c.n_u * sizeof(double), in_kind, c.stream));
+  if (c.reordered()) {
+    c.ro_in2.ensure((size_t)c.n_u);
+    FNP_CUDA(cudaMemcpyAsync(c.ro_in2.p, b_u, c.n_u * sizeof(double), in_kind, c.stream));
+    vec_gather(c, c.n_u, c.d_u_perm.p, c.ro_in2.p, bs.p);
+  } else {
+    FNP_CUDA(cudaMemcpyAsync(bs.p, b_u, c.n_u * sizeof(double), in_kind, c.stream));
+  }
   FNP_CUDA(cudaMemcpyAsync(bs.p + c.n_u, b_p, c.n_p * sizeof(double), in_kind, c.stream));
   int32_t its = 0, nap = 0;
   double rn = 0.0;
   solve_fgmres(c, bs.p, xs.p, &its, &rn, &nap);
-  FNP_CUDA(cudaMemcpyAsync(x_u, xs.p, c.n_u * sizeof(double), out_kind, c.stream));
+  const double *xu_src = xs.p;
+  if (c.reordered()) {
+    c.ro_in2.ensure((size_t)c.n_u);
+    vec_scatter(c, c.n_u, c.d_u_perm.p, xs.p, c.ro_in2.p);
+    xu_src = c.ro_in2.p;
+  }
+  FNP_CUDA(cudaMemcpyAsync(x_u, xu_src, c.n_u * sizeof(double), out_kind, c.stream));
   FNP_CUDA(cudaMemcpyAsync(x_p, xs.p + c.n_u, c.n_p * sizeof(double), out_kind, c.stream));
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   if (iterations) *iterations = its;
@@ -851,13 +977,14 @@ int fnp_solve_monolithic(fnp_context *ctx, const double *b, double *x, int on_de
     FNP_CUDA(cudaMemcpyAsync(mono.p, b, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     dmono = mono.p;
   }
-  vec_gather(c, c.n_u, c.is_u.p, dmono, bs.p);
+  const int64_t *isu = c.reordered() ? c.d_is_u_re.p : c.is_u.p;
+  vec_gather(c, c.n_u, isu, dmono, bs.p);
   vec_gather(c, c.n_p, c.is_p.p, dmono, bs.p + c.n_u);
   int32_t its = 0, nap = 0;
   double rn = 0.0;
   solve_fgmres(c, bs.p, xs.p, &its, &rn, &nap);
   double *dout = on_device ? x : mono.p;
-  vec_scatter(c, c.n_u, c.is_u.p, xs.p, dout);
+  vec_scatter(c, c.n_u, isu, xs.p, dout);
   vec_scatter(c, c.n_p, c.is_p.p, xs.p + c.n_u, dout);
   if (!on_device) FNP_CUDA(cudaMemcpyAsync(x, mono.p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   FNP_CUDA(cudaStreamSynchronize(c.stream));
@@ -946,7 +1073,10 @@ int fnp_amg_vcycle(fnp_context *ctx, int which, const double *b, double *x, int 
   Staged s(c, on_device != 0);
   const double *db = s.in(b, n);
   double *dx = s.out(x, n);
-  amg_vcycle(c, H, db, dx);
+  const bool ru = c.reordered() && (which == FNP_MAT_A00 || which == FNP_MAT_P00);
+  double *ix = ru ? u_internal_out(c, dx) : dx;
+  amg_vcycle(c, H, ru ? u_to_internal(c, db, c.ro_in) : db, ix);
+  if (ru) u_to_user(c, ix, dx);
   s.finish();
   FNP_API_END
 }

@@ -412,6 +412,17 @@ struct Ctx {
   std::vector<DevBuf<double>> V, Z;
   DevBuf<double> kr_w, kr_x, kr_b;
   DevBuf<double> sol_x, sol_b, sol_m;   // staging of the user's b / x (split and monolithic layouts)
+  // Opt-in internal numbering of the velocity dofs (option fnp_reorder_nodes = window in dofs, 0 = off;
+  // single rank): dofs sorted by row length inside windows -- the SELL row order used as the vector
+  // numbering, so that a slice's rows AND gathered columns are consecutive (profiles/sell_gather_model.py).
+  // Operators are permuted at ingestion, user vectors at the entry / exit of every call.
+  int reorder = 0;
+  std::vector<int64_t> u_perm, u_inv;           // internal dof -> user dof, user dof -> internal dof
+  DevBuf<int64_t> d_u_perm, d_is_u_re;          // device copies: u_perm, is_u composed with u_perm
+  std::vector<int64_t> h_is_u;                  // host copy of the monolithic index set of the velocity dofs
+  std::vector<int64_t> rmap[FNP_MAT_COUNT];     // internal entry -> user entry of the operators that were permuted
+  DevBuf<double> ro_in, ro_in2, ro_out;         // permuted copies of user vectors
+  bool reordered() const { return !u_perm.empty(); }
   std::vector<double> res_hist;
 
   // timers

@@ -446,3 +446,33 @@ def test_lagged_hierarchy_refresh():
         its[lag] = n
         ctx.close()
     assert its[3] <= 1.5 * its[1]                        # stale coarse levels cost a few iterations (54 -> 67 here)
+
+
+def test_internal_renumbering_option():
+    """fnp_reorder_nodes (opt-in): the velocity dofs are renumbered inside the library (row-length
+    sorted windows); callers keep their numbering.  SpMVs, the split and the monolithic solve must
+    be unaffected: same products, same iteration count, Kronecker mode still detected."""
+    p0, _ = problems.backward_facing_step(3, variant="BRM2")
+    x = pa.direct_solver(p0.system_matrix())(p0.rhs())
+    prob, _ = problems.backward_facing_step(3, variant="BRM2", wind=x[:p0.n_u].reshape(-1, 2), stabilise=True)
+    rng = np.random.default_rng(0)
+    xu, xp = rng.standard_normal(prob.n_u), rng.standard_normal(prob.n_p)
+    A, b = prob.system_matrix(), prob.rhs()
+    mono = np.empty(prob.n_u + prob.n_p)
+    mono[prob.is_u], mono[prob.is_p] = prob.b_u, prob.b_p
+    its = {}
+    for tag, extra in (("default", {}), ("reordered", {"fnp_reorder_nodes": 384})):
+        ctx = make_context(prob, extra)
+        try:
+            assert ctx.block_size(capi.MAT_A00) == 2
+            assert relerr(ctx.spmv(capi.MAT_A00, xu, prob.n_u), prob.A00 @ xu) <= TOL_SPMV
+            assert relerr(ctx.spmv(capi.MAT_A01, xp, prob.n_u), prob.A01 @ xp) <= TOL_SPMV
+            assert relerr(ctx.spmv(capi.MAT_A10, xu, prob.n_p), prob.A10 @ xu) <= TOL_SPMV
+            su, sp_, n, rn, _ = ctx.solve(prob.b_u, prob.b_p)
+            assert np.linalg.norm(b - A @ np.concatenate([su, sp_])) <= 1.05e-6 * np.linalg.norm(b)
+            xm, nm, _, _ = ctx.solve_monolithic(mono)
+            assert nm == n and np.allclose(xm[prob.is_u], su, rtol=0, atol=1e-12 * np.linalg.norm(su))
+            its[tag] = n
+        finally:
+            ctx.close()
+    assert abs(its["reordered"] - its["default"]) <= 1
