@@ -37,6 +37,50 @@ def set_iterative_options(prefix, variant):
     o.setValue("fieldsplit_p_PCD_Mp_pc_type", "jacobi")
 
 
+def test_allow_only_one_call_contract_of_reference_unit_test():
+    """The checks of the reference's test/unit/test_utils.py::test_allow_only_one_call, against the
+    drop-in helper: docstrings survive, arguments pass through, every decorated method has its own
+    once-only flag, undecorated methods are untouched."""
+    from fenapack.utils import allow_only_one_call        # the alias package, as the reference imports it
+
+    class C(object):
+        @allow_only_one_call
+        def foo(self, *args, **kwargs):
+            """Foo"""
+            return args, kwargs
+
+        @allow_only_one_call
+        def bar(self, *args, **kwargs):
+            """Bar"""
+            return args, kwargs
+
+        def baz(self, *args, **kwargs):
+            """Baz"""
+            return args, kwargs
+    o = C()
+    assert (o.foo.__doc__, o.bar.__doc__, o.baz.__doc__) == ("Foo", "Bar", "Baz")
+    expect = ((1, 2, 3), {"four": 5})
+    assert o.foo(1, 2, 3, four=5) == expect and o.bar(1, 2, 3, four=5) == expect and o.baz(1, 2, 3, four=5) == expect
+    for method in (o.foo, o.bar):
+        with pytest.raises(RuntimeError):
+            method(1, 2, 3, four=5)
+    assert o.baz(1, 2, 3, four=5) == expect
+
+
+def test_reference_module_paths_resolve_to_the_dropin_classes():
+    """``from fenapack.preconditioners import PCDPC_BRM1`` etc. -- the reference's module layout."""
+    import importlib
+    for mod, names in (("preconditioners", ("BasePCDPC", "PCDPC_BRM1", "PCDPC_BRM2", "BasePCDRPC", "PCDRPC_BRM1", "PCDRPC_BRM2")),
+                       ("field_split", ("PCDKSP", "PCDKrylovSolver")), ("field_split_backend", ("PCDInterface",)),
+                       ("assembling", ("PCDAssembler", "PCDForm")),
+                       ("nonlinear_solvers", ("PCDNewtonSolver", "PCDNonlinearProblem")),
+                       ("stabilization", ("StabilizationParameterSD",)), ("utils", ("allow_only_one_call",))):
+        alias = importlib.import_module("fenapack." + mod)
+        impl = importlib.import_module("fenapack_b200." + mod)
+        for name in names:
+            assert getattr(alias, name) is getattr(impl, name), (mod, name)
+
+
 def test_allow_only_one_call_and_public_names():
     from fenapack_b200.utils import allow_only_one_call
 
