@@ -292,3 +292,67 @@ def build_hierarchy_kron(A, bs=1, blocks=None, **kw):
     H.coarse_inv = np.kron(Hs.coarse_inv, np.eye(bs))
     H.begins = Hs.begins
     return H
+
+
+# --------------------------------------------------------------------------
+# numeric refresh with frozen prolongators (prototype of the device-side refresh)
+# --------------------------------------------------------------------------
+
+
+def galerkin_plan(A, P):
+    """(pattern of A_c, W) with ``A_c.data == W @ A.data`` for every matrix that has A's pattern:
+    the Galerkin product P^T A P with P frozen is linear in the values of A, entry (I, J) of A_c
+    collecting p_iI * a_ij * p_jJ over the fine entries (i, j).  W has one row per stored entry of
+    A_c and one column per stored entry of A, so a value refresh of the coarse operator is ONE
+    SpMV-class pass (deterministic, no atomics) -- the formulation the device-side refresh uses.
+    The pattern of A_c is the structural product (no entry is lost to cancellation)."""
+    A = sp.csr_matrix(A)
+    P = sp.csr_matrix(P)
+    A.sort_indices()
+    P.sort_indices()
+    n = A.shape[0]
+    rows = np.repeat(np.arange(n), np.diff(A.indptr))
+    cols = A.indices
+    ci = np.diff(P.indptr)[rows]                      # |P row i| per fine entry
+    cj = np.diff(P.indptr)[cols]                      # |P row j|
+    nt = ci * cj                                      # terms per fine entry
+    e = np.repeat(np.arange(A.nnz), nt)               # fine entry of every term
+    t = np.arange(nt.sum()) - np.repeat(np.cumsum(nt) - nt, nt)       # running index inside the entry
+    a = t // np.repeat(cj, nt)                        # which entry of P row i
+    b = t % np.repeat(cj, nt)                         # which entry of P row j
+    pi = P.indptr[rows[e]] + a
+    pj = P.indptr[cols[e]] + b
+    I, J, coef = P.indices[pi], P.indices[pj], P.data[pi] * P.data[pj]
+    nc = P.shape[1]
+    pat = sp.csr_matrix((np.ones(I.size), (I, J)), shape=(nc, nc))   # duplicates summed: structural pattern
+    pat.sort_indices()
+    # position of (I, J) in the CSR of the pattern
+    key = I.astype(np.int64) * nc + J
+    prow = np.repeat(np.arange(nc), np.diff(pat.indptr))
+    pkey = prow.astype(np.int64) * nc + pat.indices
+    pos = np.searchsorted(pkey, key)
+    W = sp.csr_matrix((coef, (pos, e)), shape=(pat.nnz, A.nnz))
+    W.sum_duplicates()
+    return pat, W
+
+
+def refresh_plans(H):
+    """Plans of every level transition of a hierarchy built with ``coarse_drop = 0``."""
+    return [galerkin_plan(l.A, l.P) for l in H.levels[:-1]]
+
+
+def refresh_hierarchy(H, A_new, plans, new_rho=True):
+    """Hierarchy for new values on level 0 (same pattern), prolongators frozen, coarse operators
+    recomputed through the plans.  ``new_rho``: re-estimate the smoother bounds on every level."""
+    A = sp.csr_matrix(A_new)
+    A.sort_indices()
+    out = Hierarchy(smooth_steps=H.smooth_steps, eig_ratio=H.eig_ratio)
+    for k, old in enumerate(H.levels):
+        diag = A.diagonal()
+        dinv = np.where(diag != 0.0, 1.0 / np.where(diag != 0.0, diag, 1.0), 0.0)
+        out.levels.append(Level(A=A, dinv=dinv, rho=estimate_rho(A, dinv) if new_rho else old.rho, P=old.P, R=old.R))
+        if k + 1 < len(H.levels):
+            pat, W = plans[k]
+            A = sp.csr_matrix((W @ A.data, pat.indices, pat.indptr), shape=pat.shape)
+    out.coarse_inv = np.linalg.inv(out.levels[-1].A.toarray())
+    return out

@@ -199,3 +199,29 @@ def test_streamline_diffusion_parameter_matches_oracle_assembler():
     assert np.array_equal(got, delta)
     # density scales the Peclet number only
     assert np.count_nonzero(StabilizationParameterSD(wmid, nu, 0.5).eval_cells(space.cell_diameter())) <= np.count_nonzero(got)
+
+
+def test_frozen_prolongator_refresh_is_one_linear_pass_and_keeps_the_iteration_count():
+    """Prototype of the device-side numeric refresh: with frozen prolongators
+    the coarse operators are linear in the fine values, A_c.data = W @ A.data (oracle.amg.galerkin_plan).
+    Exact to rounding, and -- unlike keeping stale coarse levels (pc_amg_lag) -- as good as a rebuild:
+    BFS level 3, hierarchy built for half the wind, refreshed for the full wind."""
+    p0, _ = problems.backward_facing_step(3, variant="BRM1")
+    x = pa.direct_solver(p0.system_matrix())(p0.rhs())
+    w = x[:p0.n_u].reshape(-1, 2)
+    p1, _ = problems.backward_facing_step(3, variant="BRM1", wind=0.5 * w)
+    p2, _ = problems.backward_facing_step(3, variant="BRM1", wind=w)
+    H1 = amg.build_hierarchy_kron(p1.A00, bs=2)
+    plans = amg.refresh_plans(H1)
+    Hr = amg.refresh_hierarchy(H1, p2.A00, plans, new_rho=False)
+    for k in range(1, len(Hr.levels)):
+        prev = Hr.levels[k - 1]
+        G = (prev.R @ (prev.A @ prev.P)).tocsr()
+        assert abs(G - Hr.levels[k].A).max() <= 1e-14 * abs(G).max()
+        assert Hr.levels[k].P is H1.levels[k].P
+
+    def its(Hu):
+        pc = pa.PCDPreconditioner(p2, "iterative", amg_u=Hu, amg_p=amg.build_hierarchy(p2.Ap))
+        return pa.fgmres(p2.system_matrix(), pc, p2.rhs(), rtol=1e-6, restart=150)[1]
+    rebuilt, refreshed = its(amg.build_hierarchy_kron(p2.A00, bs=2)), its(Hr)
+    assert refreshed <= rebuilt + 5          # measured: 54 (rebuild), 57 (refresh), 67 (stale coarse levels)
