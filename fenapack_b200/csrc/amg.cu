@@ -76,6 +76,9 @@ void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0
   const size_t L = H.host.levels.size();
   H.levels.clear();
   H.levels.resize(L);
+  H.refresh_W.clear();          // plans of the device-side refresh belong to the old hierarchy
+  H.refresh_diag.clear();
+  H.refresh_built = false;
   for (size_t l = 0; l < L; ++l) {
     const HostLevel &hl = H.host.levels[l];
     DevLevel &dl = H.levels[l];

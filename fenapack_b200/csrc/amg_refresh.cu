@@ -1,0 +1,132 @@
+// Device-side numeric refresh of an AMG hierarchy with frozen prolongators.
+//
+// With P frozen, A_c = P^T A P is linear in the values of A: A_c.val = W * A.val with the plan
+// matrix W of galerkin_plan.hpp.  W is built once per hierarchy on the host, re-indexed to the
+// positions of the device value arrays (CSR order or SELL-padded order) and uploaded like any other
+// operator, so that refreshing a level is one spmv_store on device-resident values -- deterministic,
+// no atomics -- followed by a Jacobi-diagonal kernel.  The smoother bounds rho are kept (measured
+// irrelevant in the oracle prototype: DESIGN.md section 8 item 4), the dense coarsest-level inverse
+// is recomputed on the host from the few hundred rows it has.
+//
+// EXPERIMENTAL (option pc_amg_refresh galerkin, single rank): written after the round-1 GPU budget
+// was spent; the host logic is covered on the CPU (tests/test_host_logic.py), the device path is
+// first exercised by tests/test_gpu_parity.py::test_device_side_galerkin_refresh under
+// FNP_EXPERIMENTAL_TESTS=1.
+#include "fnp_internal.cuh"
+#include "galerkin_plan.hpp"
+
+namespace fnp {
+
+void host_dense_inverse(const HostCsr &A, std::vector<double> &inv);
+
+static double *dev_values(DevCsr &A) { return A.sell ? A.sl_val.p : A.val.p; }
+static int64_t dev_nvalues(const DevCsr &A) { return A.sell ? A.sell_entries : A.nnz; }
+static int64_t dev_position(const DevCsr &A, int64_t k) { return A.sell ? (int64_t)A.sell_pos[(size_t)k] : k; }
+
+__global__ void refresh_dinv_kernel(int64_t n, const int32_t *__restrict__ diagpos, const double *__restrict__ val,
+                                    double *__restrict__ dinv, int bs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double d = diagpos[i] >= 0 ? val[diagpos[i]] : 0.0;
+  const double r = d != 0.0 ? 1.0 / d : 0.0;
+  for (int b = 0; b < bs; ++b) dinv[i * bs + b] = r;
+}
+
+static void build_plans(Ctx &c, DevHierarchy &H) {
+  const size_t L = H.levels.size();
+  H.refresh_W.clear();
+  H.refresh_diag.clear();
+  H.refresh_W.resize(L - 1);
+  H.refresh_diag.resize(L - 1);
+  for (size_t l = 0; l + 1 < L; ++l) {
+    const HostLevel &hf = H.host.levels[l], &hc = H.host.levels[l + 1];
+    GalerkinPlan plan;
+    try {
+      build_galerkin_plan(hf.A, hf.P, hf.R, hc.A, plan);
+    } catch (const std::exception &e) {
+      throw Error(FNP_ERR_STATE, e.what());
+    }
+    DevCsr &Af = H.levels[l].A(), &Ac = H.levels[l + 1].A();
+    FNP_REQUIRE(plan.terms() < (int64_t)INT32_MAX, FNP_ERR_ARG, "Galerkin refresh plan exceeds 2^31 terms");
+    // W re-indexed: row = device position of the coarse entry, column = device position of the fine entry
+    HostCsr W;
+    W.nrows = dev_nvalues(Ac);
+    W.ncols = dev_nvalues(Af);
+    W.rowptr.assign((size_t)W.nrows + 1, 0);
+    const int64_t nq = hc.A.nnz();
+    for (int64_t q = 0; q < nq; ++q) W.rowptr[(size_t)dev_position(Ac, q) + 1] = (int32_t)(plan.ptr[q + 1] - plan.ptr[q]);
+    for (int64_t r = 0; r < W.nrows; ++r) W.rowptr[(size_t)r + 1] += W.rowptr[(size_t)r];
+    W.col.resize((size_t)plan.terms());
+    W.val.resize((size_t)plan.terms());
+#pragma omp parallel for schedule(static)
+    for (int64_t q = 0; q < nq; ++q) {
+      int64_t dst = W.rowptr[(size_t)dev_position(Ac, q)];
+      for (int64_t t = plan.ptr[q]; t < plan.ptr[q + 1]; ++t, ++dst) {
+        W.col[(size_t)dst] = (int32_t)dev_position(Af, plan.src[(size_t)t]);
+        W.val[(size_t)dst] = plan.coef[(size_t)t];
+      }
+    }
+    csr_upload_pattern(c, H.refresh_W[l], W, "refresh/W" + std::to_string(l));
+    csr_set_values(c, H.refresh_W[l], W, W.val.data(), false);
+    std::vector<int32_t> dp((size_t)hc.A.nrows, -1);
+    for (int64_t i = 0; i < hc.A.nrows; ++i)
+      for (int32_t k = hc.A.rowptr[i]; k < hc.A.rowptr[i + 1]; ++k)
+        if (hc.A.col[k] == i) dp[(size_t)i] = (int32_t)dev_position(Ac, k);
+    H.refresh_diag[l].upload(dp.data(), dp.size(), c.stream);
+  }
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  H.refresh_built = true;
+}
+
+void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs, const HostCsr &level0_host) {
+  FNP_REQUIRE(H.built && !H.levels.empty(), FNP_ERR_STATE, "AMG hierarchy not built");
+  FNP_REQUIRE(c.nranks == 1 && !H.tail, FNP_ERR_OPTION, "pc_amg_refresh galerkin is available on single-rank contexts only");
+  FNP_REQUIRE(H.params.coarse_drop == 0.0, FNP_ERR_OPTION, "pc_amg_refresh galerkin needs pc_amg_coarse_drop 0");
+  const size_t L = H.levels.size();
+  StageTimer t(c, "FENaPack: AMG Galerkin refresh");
+  if (L > 1 && !H.refresh_built) build_plans(c, H);
+  for (size_t l = 0; l + 1 < L; ++l) {
+    DevCsr &Af = H.levels[l].A(), &Ac = H.levels[l + 1].A();
+    spmv_store(c, H.refresh_W[l], dev_values(Af), dev_values(Ac));
+    const int64_t n = Ac.nrows;
+    refresh_dinv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(n, H.refresh_diag[l].p, dev_values(Ac), Ac.dinv.p, bs);
+    c.launches++;
+    FNP_CUDA(cudaPeekAtLastError());
+  }
+  // host copies follow (introspection, later rebuilds) and the coarsest level is inverted again
+  if (level0_host.val.size() == H.host.levels[0].A.val.size()) H.host.levels[0].A.val = level0_host.val;
+  std::vector<double> buf;
+  for (size_t l = 1; l < L; ++l) {
+    DevCsr &A = H.levels[l].A();
+    HostCsr &h = H.host.levels[l].A;
+    buf.resize((size_t)dev_nvalues(A));
+    FNP_CUDA(cudaMemcpyAsync(buf.data(), dev_values(A), buf.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    FNP_CUDA(cudaStreamSynchronize(c.stream));
+    for (int64_t k = 0; k < h.nnz(); ++k) h.val[(size_t)k] = buf[(size_t)dev_position(A, k)];
+    for (int64_t i = 0; i < h.nrows; ++i) {
+      double d = 0.0;
+      for (int32_t k = h.rowptr[i]; k < h.rowptr[i + 1]; ++k)
+        if (h.col[k] == i) d = h.val[k];
+      H.host.levels[l].dinv[(size_t)i] = d != 0.0 ? 1.0 / d : 0.0;
+    }
+  }
+  if (L > 1) {
+    const HostCsr &hc = H.host.levels.back().A;
+    host_dense_inverse(hc, H.host.coarse_inv);
+    const int64_t nc = hc.nrows, cols = H.host.coarse_cols;
+    FNP_REQUIRE(cols == nc, FNP_ERR_STATE, "unexpected coarse inverse shape");
+    if (bs == 1) {
+      H.coarse_inv.upload(H.host.coarse_inv.data(), H.host.coarse_inv.size(), c.stream);
+    } else {
+      std::vector<double> inv((size_t)H.coarse_n * H.coarse_cols, 0.0);
+      for (int64_t i = 0; i < nc; ++i)
+        for (int64_t j = 0; j < cols; ++j)
+          for (int b = 0; b < bs; ++b)
+            inv[(size_t)(i * bs + b) * H.coarse_cols + j * bs + b] = H.host.coarse_inv[(size_t)i * cols + j];
+      H.coarse_inv.upload(inv.data(), inv.size(), c.stream);
+    }
+    FNP_CUDA(cudaStreamSynchronize(c.stream));
+  }
+}
+
+}  // namespace fnp

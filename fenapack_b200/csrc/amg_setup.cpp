@@ -409,6 +409,7 @@ static void dense_inverse(const HostCsr &A, std::vector<double> &inv) {
 
 void host_spgemm(const HostCsr &A, const HostCsr &B, HostCsr &C) { spgemm(A, B, C); }
 void host_transpose(const HostCsr &A, HostCsr &T) { transpose(A, T); }
+void host_dense_inverse(const HostCsr &A, std::vector<double> &inv) { dense_inverse(A, inv); }
 
 // helpers from dist.cu
 std::vector<int64_t> comm_ranges(Ctx &c, int64_t n_local);

@@ -157,6 +157,10 @@ static void set_inner_option(InnerOpts &o, const std::string &full, const std::s
     o.amg.theta = parse_real(full, v);
   } else if (key == "pc_amg_levels") {
     o.amg.max_levels = parse_int(full, v);
+  } else if (key == "pc_amg_refresh") {
+    if (v == "rebuild") o.amg.refresh = 0;
+    else if (v == "galerkin") o.amg.refresh = 1;
+    else throw Error(FNP_ERR_OPTION, "pc_amg_refresh: rebuild | galerkin");
   } else if (key == "pc_amg_coarse_size") {
     o.amg.coarse_size = parse_int(full, v);
   } else if (key == "pc_amg_smooth_steps") {

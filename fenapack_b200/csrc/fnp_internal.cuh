@@ -238,6 +238,8 @@ struct AmgParams {
                                      // coarsened/applied redundantly on every rank.  Off by default: +6 % at N=2
                                      // but slower (and 27 instead of 20 iterations) at N=8 with 300000
   double coarse_drop = 0.0;    // > 0: lump coarse entries below drop*sqrt(|a_ii||a_jj|) onto the diagonal
+  int refresh = 0;             // value refresh of an existing hierarchy: 0 rebuild on the host (or lag),
+                               // 1 frozen prolongators + Galerkin values recomputed on the device (amg_refresh.cu)
 };
 
 struct HostLevel {
@@ -285,9 +287,16 @@ struct DevHierarchy {
   AmgParams params;
   HostHierarchy host;     // kept for introspection / refresh
   bool built = false;
+  // device-side Galerkin refresh (amg_refresh.cu): plan matrices W_l with A_{l+1}.val = W_l * A_l.val,
+  // diagonal positions of the coarse levels
+  std::vector<DevCsr> refresh_W;
+  std::vector<DevBuf<int32_t>> refresh_diag;
+  bool refresh_built = false;
 };
 
 void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0, int bs);
+// new values on level 0 (same pattern): coarse operators recomputed on the device with frozen P
+void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs, const HostCsr &level0_host);
 // x = Vcycle(b), zero initial guess; b and x are level-0 sized device vectors (may not alias)
 void amg_vcycle(Ctx &c, DevHierarchy &H, const double *b, double *x);
 

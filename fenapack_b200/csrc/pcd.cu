@@ -262,7 +262,10 @@ void setup_all(Ctx &c) {
     // always follows the new values; the coarse levels may be kept for `lag` refreshes
     const bool same_shape = c.amg_u.built && !c.amg_u.levels.empty() && c.amg_u.levels[0].Ap == &c.dmat[uidx] &&
                             c.amg_u.host.levels[0].A.nrows == c.dmat[uidx].nrows;
-    if (same_shape && c.amg_u_age + 1 < c.opt_u.amg.lag) {
+    if (same_shape && c.opt_u.amg.refresh == 1 && c.nranks == 1) {
+      // frozen prolongators, Galerkin values recomputed on the device (amg_refresh.cu)
+      amg_refresh_device(c, c.amg_u, c.kron_bs[uidx], c.hmat[uidx]);
+    } else if (same_shape && c.amg_u_age + 1 < c.opt_u.amg.lag) {
       ++c.amg_u_age;
     } else {
       build_amg(c, uidx, c.amg_u, c.opt_u.amg);

@@ -98,7 +98,9 @@ int fnp_synchronize(fnp_context *ctx);
  *   ..._pc_type jacobi
  *   <prefix>pc_amg_threshold, pc_amg_levels, pc_amg_coarse_size, pc_amg_smooth_steps,
  *   pc_amg_eig_ratio, pc_amg_prolongator_truncation, pc_amg_coarse_drop, pc_amg_replicate_size,
- *   pc_amg_lag (velocity block: rebuild the coarse levels at every lag-th refresh only) for the prefixes fieldsplit_u_ and fieldsplit_p_PCD_Ap_
+ *   pc_amg_lag (velocity block: rebuild the coarse levels at every lag-th refresh only),
+ *   pc_amg_refresh rebuild|galerkin (velocity block, experimental: on a value refresh keep the prolongators and
+ *   recompute the coarse operators on the device) for the prefixes fieldsplit_u_ and fieldsplit_p_PCD_Ap_
  * "hypre"/"boomeramg"/"gamg" are accepted as aliases of amg (the smoothed-
  * aggregation hierarchy of this library).  Unknown names -> FNP_ERR_OPTION.
  * Library tuning knobs (prefix fnp_, not PETSc names): fnp_timers, fnp_cuda_graph, fnp_spmv_kernel

@@ -2,6 +2,8 @@
 the same seeded inputs.  Tolerances are BASELINE.json's: SpMV and the
 fixed-iteration Chebyshev-Jacobi apply <= 1e-12 relative, full PC apply <= 1e-8
 relative, outer FGMRES iteration counts within +-1 at the same final residual."""
+import os
+
 import numpy as np
 import pytest
 
@@ -476,3 +478,40 @@ def test_internal_renumbering_option():
         finally:
             ctx.close()
     assert abs(its["reordered"] - its["default"]) <= 1
+
+
+@pytest.mark.skipif(os.environ.get("FNP_EXPERIMENTAL_TESTS") != "1",
+                    reason="device path written after the round-1 GPU budget was spent; enable with FNP_EXPERIMENTAL_TESTS=1")
+def test_device_side_galerkin_refresh():
+    """pc_amg_refresh galerkin: after a value refresh the prolongators are kept and the coarse
+    operators are recomputed on the device, A_c.val = W * A.val (csrc/amg_refresh.cu).  The coarse
+    levels must equal P^T A P of the new level-0 operator and the solve must converge about as fast
+    as with a rebuilt hierarchy (oracle prototype: 57 vs 54 iterations, 67 with stale coarse levels)."""
+    p0, _ = problems.backward_facing_step(3, variant="BRM1")
+    x = pa.direct_solver(p0.system_matrix())(p0.rhs())
+    w = x[:p0.n_u].reshape(-1, 2)
+    p1, _ = problems.backward_facing_step(3, variant="BRM1", wind=0.5 * w)
+    p2, _ = problems.backward_facing_step(3, variant="BRM1", wind=w)
+    its = {}
+    for mode in ("rebuild", "galerkin"):
+        ctx = make_context(p1, {"fieldsplit_u_pc_amg_refresh": mode})
+        try:
+            before, _ = ctx.amg_hierarchy(capi.MAT_A00)
+            ctx.set_values(capi.MAT_A00, p2.A00.data)
+            ctx.set_values(capi.MAT_KP, p2.Kp.data)
+            ctx.setup()
+            after, cinv = ctx.amg_hierarchy(capi.MAT_A00)
+            if mode == "galerkin":
+                assert len(after) == len(before)
+                for k in range(len(after) - 1):
+                    assert abs(after[k]["P"] - before[k]["P"]).max() == 0.0          # frozen
+                    G = (after[k]["P"].T @ (after[k]["A"] @ after[k]["P"])).tocsr()
+                    assert abs(G - after[k + 1]["A"]).max() <= 1e-12 * abs(G).max()
+                assert relerr(cinv, np.linalg.inv(after[-1]["A"].toarray())) <= 1e-9
+            xu, xp, n, rn, _ = ctx.solve(p2.b_u, p2.b_p)
+            A, b = p2.system_matrix(), p2.rhs()
+            assert np.linalg.norm(b - A @ np.concatenate([xu, xp])) <= 2e-6 * np.linalg.norm(b)
+            its[mode] = n
+        finally:
+            ctx.close()
+    assert its["galerkin"] <= its["rebuild"] + 6
