@@ -364,7 +364,8 @@ struct Ctx {
   DevCsr rp;
   DevHierarchy amg_rp;
   int spmv_mode = 0;            // 0 auto (by row-length histogram), 1 CSR vector kernel always, 2 SELL always
-  int sell_gather = 15;         // SELL kernel variant bits (kernels.cu): 1 wide gathers, 2 six CTAs/SM, 4 L2 prefetch, 8 wide epilogue
+  int sell_gather = 15;         // SpMV kernel variant bits (kernels.cu): 1 wide gathers, 2 six CTAs/SM, 4 L2 prefetch, 8 wide epilogue (SELL);
+                                // 16 L2 prefetch in the CSR sub-warp kernel (experimental)
   int sell_sigma = 1024;        // SELL sorting window (rows)
   double sell_max_mean_row = 64.0;   // auto: operators with a longer mean row keep CSR + sub-warp per row
   int timers_on = 0;            // 0 off, 1 stage timers, 2 also one timer per SpMV launch

@@ -72,7 +72,10 @@ __device__ __forceinline__ void gather3_wide(const double *__restrict__ p, doubl
   a2 = odd ? hi.y : hi.x;
 }
 
-template <int LANES, int BS, class Epi>
+// PF (option fnp_sell_gather bit 16, experimental, off by default): lane 0 of every warp pulls the
+// contiguous (col, val) range of the warp's 32 / LANES rows into L2 with two bulk prefetches, as the
+// SELL kernel does for its slice (the ends are trimmed to 16-byte boundaries: a prefetch is a hint).
+template <int LANES, int BS, class Epi, bool PF>
 __global__ void __launch_bounds__(256)
 spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             const double *__restrict__ val, const double *__restrict__ x, const double *__restrict__ xg, int nown,
@@ -80,6 +83,13 @@ spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__rest
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = tid / LANES;
   const int lane = tid % LANES;
+  if (PF && (threadIdx.x & 31) == 0 && row < nrows) {
+    const int k0 = rowptr[row], k1 = rowptr[min(row + 32 / LANES, nrows)];
+    const int c0 = (k0 + 3) & ~3, c1 = k1 & ~3;
+    if (c1 > c0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(col + c0), "r"((c1 - c0) * 4) : "memory");
+    const int v0 = (k0 + 1) & ~1, v1 = k1 & ~1;
+    if (v1 > v0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(val + v0), "r"((v1 - v0) * 8) : "memory");
+  }
   double s0[BS], s1[BS];
 #pragma unroll
   for (int b = 0; b < BS; ++b) s0[b] = s1[b] = 0.0;
@@ -520,8 +530,13 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
   }
   if (A.halo) halo_wait(c, *A.halo, c.stream);
   auto grid = [&](int lanes) { return (int)(((int64_t)A.nrows * lanes + threads - 1) / threads); };
-#define FNP_VEC(L) \
-  spmv_kernel<L, BS, Epi><<<grid(L), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi)
+#define FNP_VEC(L)                                                                                                        \
+  do {                                                                                                                \
+    if (c.sell_gather & 16)                                                                                           \
+      spmv_kernel<L, BS, Epi, true><<<grid(L), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi);  \
+    else                                                                                                              \
+      spmv_kernel<L, BS, Epi, false><<<grid(L), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); \
+  } while (0)
   switch (A.lanes) {
     case 2: FNP_VEC(2); break;
     case 4: FNP_VEC(4); break;
