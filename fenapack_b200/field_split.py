@@ -28,7 +28,8 @@ from .utils import allow_only_one_call
 
 _OUTER_KEYS = ("ksp_type", "ksp_gmres_restart", "ksp_rtol", "ksp_atol", "ksp_max_it")
 _U_KEYS = ("ksp_type", "ksp_max_it", "pc_type", "pc_hypre_type", "pc_amg_threshold", "pc_amg_levels",
-           "pc_amg_coarse_size", "pc_amg_smooth_steps", "pc_amg_eig_ratio", "pc_amg_coarse_drop", "pc_amg_prolongator_truncation", "pc_amg_replicate_size", "pc_amg_lag")
+           "pc_amg_coarse_size", "pc_amg_smooth_steps", "pc_amg_eig_ratio", "pc_amg_coarse_drop", "pc_amg_prolongator_truncation", "pc_amg_replicate_size", "pc_amg_lag",
+           "pc_amg_refresh")
 
 
 def dofmap_dofs_is(dofmap):
@@ -105,6 +106,11 @@ class PCDKSP(object):
             val = opts.getString(key, None)
             if val is not None:
                 self._outer_opts[key] = val
+        # library tuning knobs (<prefix>fnp_*: not PETSc names, include/fenapack_cuda.h) pass through
+        for name, val in PETSc.Options().getAll().items():
+            name = name.lstrip("-")
+            if name.startswith(self._prefix + "fnp_"):
+                self._outer_opts[name[len(self._prefix):]] = val
         uopts = PETSc.Options(self._prefix + "fieldsplit_u_")
         for key in _U_KEYS:
             val = uopts.getString(key, None)

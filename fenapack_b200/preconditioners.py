@@ -27,7 +27,8 @@ from ._backend import PETSc
 
 _INNER_KEYS = ("ksp_type", "ksp_max_it", "ksp_rtol", "pc_type", "pc_hypre_type",
                "ksp_chebyshev_eigenvalues", "pc_amg_threshold", "pc_amg_levels",
-               "pc_amg_coarse_size", "pc_amg_smooth_steps", "pc_amg_eig_ratio", "pc_amg_coarse_drop", "pc_amg_prolongator_truncation", "pc_amg_replicate_size", "pc_amg_lag")
+               "pc_amg_coarse_size", "pc_amg_smooth_steps", "pc_amg_eig_ratio", "pc_amg_coarse_drop", "pc_amg_prolongator_truncation", "pc_amg_replicate_size", "pc_amg_lag",
+               "pc_amg_refresh")
 
 
 def _vec_array(v, readonly=False):

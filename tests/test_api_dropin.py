@@ -81,6 +81,27 @@ def test_reference_module_paths_resolve_to_the_dropin_classes():
             assert getattr(alias, name) is getattr(impl, name), (mod, name)
 
 
+def test_options_database_forwarding():
+    """What PCDKSP.setFromOptions picks up from the options database: the reference's names under the
+    user prefix, the library's own knobs (<prefix>fnp_*), and nothing else -- options of solvers the
+    library does not have (``mat_mumps_icntl_4``, ``ksp_monitor``; demo_navier-stokes-pcd.py:149-160) are
+    ignored as PETSc ignores unused options."""
+    Options.clear()
+    o = Options("baz_")
+    for k, v in (("ksp_gmres_restart", 150), ("fieldsplit_u_ksp_type", "richardson"), ("fieldsplit_u_pc_type", "hypre"),
+                 ("fieldsplit_u_mat_mumps_icntl_4", 2), ("ksp_monitor", ""), ("fnp_reorder_nodes", 3072),
+                 ("fieldsplit_u_pc_amg_refresh", "galerkin")):
+        o.setValue(k, v)
+    Options("other_").setValue("fnp_cuda_graph", 0)
+    ksp = fp.PCDKSP()
+    ksp.setOptionsPrefix("baz_")
+    ksp.setFromOptions()
+    assert ksp._outer_opts == {"ksp_type": "gmres", "ksp_gmres_restart": "150", "fnp_reorder_nodes": "3072"}
+    assert ksp._u_opts == {"fieldsplit_u_ksp_type": "richardson", "fieldsplit_u_pc_type": "hypre",
+                           "fieldsplit_u_pc_amg_refresh": "galerkin"}
+    Options.clear()
+
+
 def test_allow_only_one_call_and_public_names():
     from fenapack_b200.utils import allow_only_one_call
 
