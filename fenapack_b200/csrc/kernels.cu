@@ -145,7 +145,10 @@ constexpr int SELL_NARROW = 1;   // flag in bit 0 of a slice pointer (pointers a
 
 // Per-thread sums of one SELL row (entries k = 0 .. len-1 at stride 32).  WIDE selects the
 // 16-byte gathers (BS == 3 only); products and their order are the same in both variants.
-template <int BS, bool WIDE>
+// PIPE (BS == 3, option bit 32, experimental): the column indices of the next group of four are
+// loaded before the gathers of the current one, taking the col -> gather dependency off the critical
+// path (ncu source view of the round-1 kernel: a third of the stall samples wait on the col loads).
+template <int BS, bool WIDE, bool PIPE>
 __device__ __forceinline__ void sell_row_sums(const int32_t *__restrict__ cp, const double *__restrict__ vp, int len,
                                               const double *__restrict__ x, const double *__restrict__ xg, int nown,
                                               double (&out)[BS]) {
@@ -153,9 +156,27 @@ __device__ __forceinline__ void sell_row_sums(const int32_t *__restrict__ cp, co
 #pragma unroll
   for (int b = 0; b < BS; ++b) s0[b] = s1[b] = 0.0;
   int k = 0;
+  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  if (PIPE && len >= 4) {
+    c0 = __ldcs(cp + 0 * SELL_C);
+    c1 = __ldcs(cp + 1 * SELL_C);
+    c2 = __ldcs(cp + 2 * SELL_C);
+    c3 = __ldcs(cp + 3 * SELL_C);
+  }
   for (; k + 4 <= len; k += 4) {
-    const int c0 = __ldcs(cp + (k + 0) * SELL_C), c1 = __ldcs(cp + (k + 1) * SELL_C);
-    const int c2 = __ldcs(cp + (k + 2) * SELL_C), c3 = __ldcs(cp + (k + 3) * SELL_C);
+    if (!PIPE) {
+      c0 = __ldcs(cp + (k + 0) * SELL_C);
+      c1 = __ldcs(cp + (k + 1) * SELL_C);
+      c2 = __ldcs(cp + (k + 2) * SELL_C);
+      c3 = __ldcs(cp + (k + 3) * SELL_C);
+    }
+    int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+    if (PIPE && k + 8 <= len) {
+      n0 = __ldcs(cp + (k + 4) * SELL_C);
+      n1 = __ldcs(cp + (k + 5) * SELL_C);
+      n2 = __ldcs(cp + (k + 6) * SELL_C);
+      n3 = __ldcs(cp + (k + 7) * SELL_C);
+    }
     const double v0 = __ldcs(vp + (k + 0) * SELL_C), v1 = __ldcs(vp + (k + 1) * SELL_C);
     const double v2 = __ldcs(vp + (k + 2) * SELL_C), v3 = __ldcs(vp + (k + 3) * SELL_C);
     const double *p0 = gather_ptr<BS>(x, xg, nown, c0), *p1 = gather_ptr<BS>(x, xg, nown, c1);
@@ -181,6 +202,12 @@ __device__ __forceinline__ void sell_row_sums(const int32_t *__restrict__ cp, co
       s1[b] += v1 * x1[b];
       s0[b] += v2 * x2[b];
       s1[b] += v3 * x3[b];
+    }
+    if (PIPE) {
+      c0 = n0;
+      c1 = n1;
+      c2 = n2;
+      c3 = n3;
     }
   }
   for (; k < len; ++k) {
@@ -257,7 +284,8 @@ __device__ __forceinline__ void sell_prefetch(const int32_t *__restrict__ col, c
 }
 
 // VAR bits (option fnp_sell_gather): 1 16-byte gathers (BS == 3), 2 six CTAs per SM (40 registers),
-// 4 L2 bulk prefetch of the slice stream, 8 16-byte loads in the epilogue (BS == 3).
+// 4 L2 bulk prefetch of the slice stream, 8 16-byte loads in the epilogue (BS == 3), 32 pipelined column
+// loads (BS == 3, experimental: only 45 and 47 are instantiated).
 // Measured on A00 = S (x) I_3 of the 64^3 cavity (profiles/r01_spmv_kernel_choice.md): 0.247 ms
 // with none, 0.178 ms with the prefetch alone, 0.170 ms with all.  A persistent variant (warps
 // striding over slices, next slice prefetched) was measured 2x slower and is not kept.
@@ -295,9 +323,9 @@ spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t 
   } else {
     double s[BS];
     if (BS == 3 && (VAR & 1) && !narrow)
-      sell_row_sums<BS, BS == 3>(cp, vp, len, x, xg, nown, s);
+      sell_row_sums<BS, BS == 3, (VAR & 32) != 0>(cp, vp, len, x, xg, nown, s);
     else
-      sell_row_sums<BS, false>(cp, vp, len, x, xg, nown, s);
+      sell_row_sums<BS, false, false>(cp, vp, len, x, xg, nown, s);
     if (row >= 0) {
       if constexpr (BS == 3 && (VAR & 8) != 0) {
         epilogue3(epi, row, s, !narrow);
@@ -502,10 +530,12 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
 #define FNP_SELL(V) \
   spmv_sell_kernel<BS, Epi, V><<<grid, threads, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, epi)
       if (BS == 3) {
-        switch (c.sell_gather & 15) {
+        switch (c.sell_gather & 47) {
           case 0: FNP_SELL(0); break;
           case 4: FNP_SELL(4); break;
           case 7: FNP_SELL(7); break;
+          case 45: FNP_SELL(45); break;      // pipelined column loads, registers uncapped
+          case 47: FNP_SELL(47); break;      // pipelined column loads, 6 CTAs/SM
           default: FNP_SELL(15); break;
         }
       } else {

@@ -73,7 +73,7 @@ def time_solve(ctx, tag):
 yp = torch.empty_like(xp)
 ctx = make(1024, 0)
 out = []
-for g in (0, 4, 7, 15):
+for g in (0, 4, 7, 15, 45, 47):
     ctx.set_option("fnp_sell_gather", g)
     ms = time_spmv(ctx, capi.MAT_A00, xu, yu)
     if ref is None:
@@ -86,7 +86,7 @@ for g in (15, 31):            # bit 16: L2 prefetch in the CSR sub-warp kernel (
     ctx.set_option("fnp_sell_gather", g)
     out.append(f"| A10 g{g} {time_spmv(ctx, capi.MAT_A10, xu, yp):.4f}")
 print(" ".join(out), flush=True)
-for g in (7, 15, 31):
+for g in (7, 15, 31, 47):
     ctx.set_option("fnp_sell_gather", g)
     time_solve(ctx, f"g{g}")
     sol = torch.cat([su, sp_]).clone()
