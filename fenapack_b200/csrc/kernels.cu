@@ -306,19 +306,24 @@ spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t 
   const int32_t *cp = col + base + lane;
   const double *vp = val + base + lane;
   if (BS == 1) {
+    // VAR bit 64 (experimental): operators that fit in L2 and are applied many times per PC apply
+    // (Ap, Mp, Kp and their coarse levels) load their stream with the default cache policy instead
+    // of evict-first, so that it stays resident between the applies
+    auto ldm_i = [](const int32_t *p) { return (VAR & 64) ? __ldg(p) : __ldcs(p); };
+    auto ldm_d = [](const double *p) { return (VAR & 64) ? __ldg(p) : __ldcs(p); };
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int k = 0;
     for (; k + 4 <= len; k += 4) {
-      const int c0 = __ldcs(cp + (k + 0) * SELL_C), c1 = __ldcs(cp + (k + 1) * SELL_C);
-      const int c2 = __ldcs(cp + (k + 2) * SELL_C), c3 = __ldcs(cp + (k + 3) * SELL_C);
-      const double v0 = __ldcs(vp + (k + 0) * SELL_C), v1 = __ldcs(vp + (k + 1) * SELL_C);
-      const double v2 = __ldcs(vp + (k + 2) * SELL_C), v3 = __ldcs(vp + (k + 3) * SELL_C);
+      const int c0 = ldm_i(cp + (k + 0) * SELL_C), c1 = ldm_i(cp + (k + 1) * SELL_C);
+      const int c2 = ldm_i(cp + (k + 2) * SELL_C), c3 = ldm_i(cp + (k + 3) * SELL_C);
+      const double v0 = ldm_d(vp + (k + 0) * SELL_C), v1 = ldm_d(vp + (k + 1) * SELL_C);
+      const double v2 = ldm_d(vp + (k + 2) * SELL_C), v3 = ldm_d(vp + (k + 3) * SELL_C);
       s0 += v0 * __ldg(gather_ptr<1>(x, xg, nown, c0));
       s1 += v1 * __ldg(gather_ptr<1>(x, xg, nown, c1));
       s2 += v2 * __ldg(gather_ptr<1>(x, xg, nown, c2));
       s3 += v3 * __ldg(gather_ptr<1>(x, xg, nown, c3));
     }
-    for (; k < len; ++k) s0 += __ldcs(vp + k * SELL_C) * __ldg(gather_ptr<1>(x, xg, nown, __ldcs(cp + k * SELL_C)));
+    for (; k < len; ++k) s0 += ldm_d(vp + k * SELL_C) * __ldg(gather_ptr<1>(x, xg, nown, ldm_i(cp + k * SELL_C)));
     if (row >= 0) epilogue(epi, row, (s0 + s1) + (s2 + s3));
   } else {
     double s[BS];
@@ -539,7 +544,9 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
           default: FNP_SELL(15); break;
         }
       } else {
-        if (c.sell_gather & 4) FNP_SELL(4);
+        // bit 64: L2-resident policy for operators of at most 48 MB (Ap, Mp, Kp, coarse levels)
+        if ((c.sell_gather & 64) && BS == 1 && A.spmv_bytes() <= 48e6) FNP_SELL(68);
+        else if (c.sell_gather & 4) FNP_SELL(4);
         else FNP_SELL(0);
       }
 #undef FNP_SELL
