@@ -544,8 +544,8 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
           default: FNP_SELL(15); break;
         }
       } else {
-        // bit 64: L2-resident policy for operators of at most 48 MB (Ap, Mp, Kp, coarse levels)
-        if ((c.sell_gather & 64) && BS == 1 && A.spmv_bytes() <= 48e6) FNP_SELL(68);
+        // bit 64: L2-resident policy for operators of at most 64 MB (Ap, Mp, Kp, coarse levels)
+        if ((c.sell_gather & 64) && BS == 1 && A.spmv_bytes() <= 64e6) FNP_SELL(68);
         else if (c.sell_gather & 4) FNP_SELL(4);
         else FNP_SELL(0);
       }

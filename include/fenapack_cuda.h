@@ -107,7 +107,7 @@ int fnp_synchronize(fnp_context *ctx);
  * auto|csr|sell, fnp_sell_max_mean_row, fnp_sell_sigma (sorting window, before fnp_set_pattern),
  * fnp_sell_gather (bit mask: 1 16-byte gathers, 2 six CTAs/SM, 4 L2 bulk prefetch, 8 16-byte epilogue
  * loads, 16 L2 bulk prefetch in the CSR kernel (experimental), 32 pipelined column loads (experimental, as 45 or 47), 64 default instead of evict-first cache policy for
- * operators of at most 48 MB (experimental); default 15, results are bit-identical for every value), fnp_kronecker, fnp_prune_zeros,
+ * operators of at most 64 MB (experimental); default 15, results are bit-identical for every value), fnp_kronecker, fnp_prune_zeros,
  * fnp_halo_overlap, fnp_halo_p2p, fnp_reorder_nodes (experimental, single rank, before fnp_set_pattern:
  * window in dofs of a library-internal, row-length-sorted numbering of the velocity dofs; FNP_MAT_A00 must
  * then be the first velocity operator set; callers keep their own numbering in every call, only the AMG

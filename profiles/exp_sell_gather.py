@@ -79,7 +79,7 @@ for g in (0, 4, 7, 15, 45, 47):
     if ref is None:
         ref = yu.clone()
     out.append(f"g{g} {ms:.4f} ({float((yu - ref).abs().max()):.0e})")
-for g in (0, 4, 79):      # 79 = 15 + 64: default cache policy (L2 resident) for operators <= 48 MB
+for g in (0, 4, 79):      # 79 = 15 + 64: default cache policy (L2 resident) for operators <= 64 MB
     ctx.set_option("fnp_sell_gather", g)
     out.append(f"| A01 g{g} {time_spmv(ctx, capi.MAT_A01, xp, yu):.4f} Ap g{g} {time_spmv(ctx, capi.MAT_AP, xp, yp):.4f}")
 for g in (15, 31):            # bit 16: L2 prefetch in the CSR sub-warp kernel (A10, 181 nnz per row)
