@@ -332,3 +332,52 @@ class OseenBoxProblem:
         rp, ci, va = getattr(self, name)
         ncols = {"A00": self.n_u_global, "A10": self.n_u_global}.get(name, self.n_p_global)
         return sp.csr_matrix((va, ci, rp), shape=(rp.size - 1, ncols))
+
+
+class MergedProblem:
+    """The rows of several consecutive z-slabs (OseenBoxProblem instances generated as ranks
+    s0 .. s0+k-1 of a finer partition) as ONE local problem: row pointers chained, column ids
+    are global already.  Bounds the generator's device memory at large n (one slab of the 128^3
+    cavity needs as much as the whole 64^3 one)."""
+
+    OPS = ("A00", "A01", "A10", "Ap", "Mp", "Kp")
+
+    def __init__(self, parts):
+        p0, pl = parts[0], parts[-1]
+        for k in ("kind", "nu", "variant", "n_u_global", "n_p_global", "cheb_bounds", "ndofs_global"):
+            setattr(self, k, getattr(p0, k))
+        self.u_begin, self.p_begin = p0.u_begin, p0.p_begin
+        self.n_u = sum(p.n_u for p in parts)
+        self.n_p = sum(p.n_p for p in parts)
+        assert pl.u_begin + pl.n_u - p0.u_begin == self.n_u and pl.p_begin + pl.n_p - p0.p_begin == self.n_p
+        for name in self.OPS:
+            rps, cis, vas = zip(*[getattr(p, name) for p in parts])
+            nnz = np.cumsum([0] + [int(r[-1]) for r in rps])
+            assert nnz[-1] < 2 ** 31, "operator exceeds 2^31 entries on one rank"
+            rp = np.concatenate([rps[0]] + [r[1:].astype(np.int64) + nnz[i + 1] for i, r in enumerate(rps[1:])]).astype(np.int32)
+            setattr(self, name, (rp, np.concatenate(cis), np.concatenate(vas)))
+            for p in parts:
+                setattr(p, name, None)          # free the slab copies as we go
+        self.b_u = np.concatenate([p.b_u for p in parts])
+        self.b_p = np.concatenate([p.b_p for p in parts])
+        off = np.cumsum([0] + [p.n_p for p in parts])
+        self.bc_idx = np.concatenate([p.bc_idx.astype(np.int64) + off[i] for i, p in enumerate(parts)]).astype(np.int32)
+        self.bc_val = np.concatenate([p.bc_val for p in parts])
+
+    scipy = OseenBoxProblem.scipy
+
+
+def generate(nx, ny, nz, kind="cavity", nu=0.02, variant="BRM2", rank=0, nranks=1, device="cpu",
+             cells_per_slab=64 ** 3):
+    """Local problem of `rank`, generated in z-slabs of about `cells_per_slab` cells."""
+    k = max(1, int(np.ceil(nx * ny * nz / nranks / cells_per_slab)))
+    k = min(k, max(1, (nz + 1) // nranks))        # every slab keeps at least one vertex plane
+    if k == 1:
+        return OseenBoxProblem(nx, ny, nz, kind=kind, nu=nu, variant=variant, rank=rank, nranks=nranks, device=device)
+    parts = []
+    for s in range(k):
+        parts.append(OseenBoxProblem(nx, ny, nz, kind=kind, nu=nu, variant=variant, rank=rank * k + s,
+                                     nranks=nranks * k, device=device))
+        if str(device).startswith("cuda"):
+            torch.cuda.empty_cache()
+    return MergedProblem(parts)

@@ -66,6 +66,8 @@ SIGNATURES = {
     "fnp_amg_coarse_inverse": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "fnp_amg_vcycle": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "fnp_get_timer": (C.c_int, [C.c_void_p, C.c_char_p, _c_double_p, _c_int64_p]),
+    "fnp_get_timer_bytes": (C.c_int, [C.c_void_p, C.c_char_p, _c_double_p]),
+    "fnp_timer_names": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "fnp_reset_timers": (C.c_int, [C.c_void_p]),
     "fnp_kernel_launches": (C.c_int64, [C.c_void_p]),
     "fnp_event_tic": (C.c_int, [C.c_void_p]),
@@ -187,6 +189,10 @@ class Context:
         if which in self._shapes and values.size != self._shapes[which][1]:
             raise ValueError("value array does not match the pattern (same pattern, new values only)")
         _check(self._lib.fnp_set_values(self._h, which, _ptr(values)))
+
+    def set_values_device(self, which, device_address):
+        """Value refresh from an array that already lives in device memory (address as int)."""
+        _check(self._lib.fnp_set_values(self._h, which, _ptr(int(device_address))))
 
     def set_matrix(self, which, A):
         """Upload a scipy CSR matrix (pattern + values)."""
@@ -337,6 +343,17 @@ class Context:
         ms, calls = C.c_double(), C.c_int64()
         _check(self._lib.fnp_get_timer(self._h, name.encode(), C.byref(ms), C.byref(calls)))
         return ms.value, calls.value
+
+    def timer_bytes(self, name):
+        b = C.c_double()
+        _check(self._lib.fnp_get_timer_bytes(self._h, name.encode(), C.byref(b)))
+        return b.value
+
+    def timer_names(self):
+        n = _check(self._lib.fnp_timer_names(self._h, None, 0))
+        buf = C.create_string_buffer(n + 1)
+        _check(self._lib.fnp_timer_names(self._h, buf, n + 1))
+        return [t for t in buf.value.decode().split("\n") if t]
 
     def reset_timers(self):
         _check(self._lib.fnp_reset_timers(self._h))

@@ -143,22 +143,15 @@ void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0
     H.built = true;
     return;
   }
-  // coarsest level: dense inverse, expanded to the interleaved components
+  // coarsest level: dense inverse
   const int64_t nc = H.host.levels.back().A.nrows, cols = H.host.coarse_cols;
   H.coarse_n = (int)(nc * bs);
   H.coarse_cols = (int)(cols * bs);
   H.coarse_maxloc = (int)(H.host.coarse_maxloc * bs);
   if (c.nranks > 1) H.coarse_gather.alloc((size_t)(c.nranks + 1) * H.coarse_maxloc);
-  if (bs == 1) {
-    H.coarse_inv.upload(H.host.coarse_inv.data(), H.host.coarse_inv.size(), c.stream);
-  } else {
-    std::vector<double> inv((size_t)H.coarse_n * H.coarse_cols, 0.0);
-    for (int64_t i = 0; i < nc; ++i)
-      for (int64_t j = 0; j < cols; ++j)
-        for (int b = 0; b < bs; ++b)
-          inv[(size_t)(i * bs + b) * H.coarse_cols + j * bs + b] = H.host.coarse_inv[(size_t)i * cols + j];
-    H.coarse_inv.upload(inv.data(), inv.size(), c.stream);
-  }
+  // the scalar inverse serves the bs interleaved components (dense_gemv)
+  H.coarse_bs = bs;
+  H.coarse_inv.upload(H.host.coarse_inv.data(), H.host.coarse_inv.size(), c.stream);
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   H.built = true;
 }
@@ -181,14 +174,14 @@ static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, dou
   const bool last = l + 1 == H.levels.size();
   if (last && !H.tail) {
     if (c.nranks == 1 || H.serial) {
-      dense_gemv(c, H.coarse_n, H.coarse_cols, H.coarse_inv.p, b, x);
+      dense_gemv(c, H.coarse_n / H.coarse_bs, H.coarse_cols / H.coarse_bs, H.coarse_bs, H.coarse_inv.p, b, x);
     } else {
       // padded all-gather of the coarse right-hand side, then this rank's rows of the inverse
       double *slot = H.coarse_gather.p + (size_t)c.nranks * H.coarse_maxloc;
       FNP_CUDA(cudaMemsetAsync(slot, 0, H.coarse_maxloc * sizeof(double), c.stream));
       if (H.coarse_n) FNP_CUDA(cudaMemcpyAsync(slot, b, H.coarse_n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
       FNP_NCCL(nccl().AllGather(slot, H.coarse_gather.p, (size_t)H.coarse_maxloc, ncclDouble, c.comm, c.stream));
-      dense_gemv(c, H.coarse_n, H.coarse_cols, H.coarse_inv.p, H.coarse_gather.p, x);
+      dense_gemv(c, H.coarse_n / H.coarse_bs, H.coarse_cols / H.coarse_bs, H.coarse_bs, H.coarse_inv.p, H.coarse_gather.p, x);
     }
     return;
   }

@@ -8,10 +8,9 @@
 // irrelevant in the oracle prototype: DESIGN.md section 8 item 4), the dense coarsest-level inverse
 // is recomputed on the host from the few hundred rows it has.
 //
-// EXPERIMENTAL (option pc_amg_refresh galerkin, single rank): written after the round-1 GPU budget
-// was spent; the host logic is covered on the CPU (tests/test_host_logic.py), the device path is
-// first exercised by tests/test_gpu_parity.py::test_device_side_galerkin_refresh under
-// FNP_EXPERIMENTAL_TESTS=1.
+// Option pc_amg_refresh galerkin (the default on single-rank contexts); covered on the GPU by
+// tests/test_gpu_parity.py::test_device_side_galerkin_refresh and the refresh tests of
+// tests/test_api_dropin.py, host plan logic by tests/test_host_logic.py.
 #include "fnp_internal.cuh"
 #include "galerkin_plan.hpp"
 
@@ -78,7 +77,7 @@ static void build_plans(Ctx &c, DevHierarchy &H) {
   H.refresh_built = true;
 }
 
-void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs, const HostCsr &level0_host) {
+void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs) {
   FNP_REQUIRE(H.built && !H.levels.empty(), FNP_ERR_STATE, "AMG hierarchy not built");
   FNP_REQUIRE(c.nranks == 1 && !H.tail, FNP_ERR_OPTION, "pc_amg_refresh galerkin is available on single-rank contexts only");
   FNP_REQUIRE(H.params.coarse_drop == 0.0, FNP_ERR_OPTION, "pc_amg_refresh galerkin needs pc_amg_coarse_drop 0");
@@ -93,16 +92,46 @@ void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs, const HostCsr &level0_h
     c.launches++;
     FNP_CUDA(cudaPeekAtLastError());
   }
-  // host copies follow (introspection, later rebuilds) and the coarsest level is inverted again
-  if (level0_host.val.size() == H.host.levels[0].A.val.size()) H.host.levels[0].A.val = level0_host.val;
-  std::vector<double> buf;
-  for (size_t l = 1; l < L; ++l) {
-    DevCsr &A = H.levels[l].A();
-    HostCsr &h = H.host.levels[l].A;
-    buf.resize((size_t)dev_nvalues(A));
+  // host copies of the level values are fetched lazily (amg_sync_host: introspection, later
+  // rebuilds); only the coarsest level comes back now, to be inverted again
+  H.host_vals_stale = true;
+  if (L > 1) {
+    DevCsr &A = H.levels.back().A();
+    HostCsr &h = H.host.levels.back().A;
+    std::vector<double> buf((size_t)dev_nvalues(A));
     FNP_CUDA(cudaMemcpyAsync(buf.data(), dev_values(A), buf.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     FNP_CUDA(cudaStreamSynchronize(c.stream));
     for (int64_t k = 0; k < h.nnz(); ++k) h.val[(size_t)k] = buf[(size_t)dev_position(A, k)];
+  }
+  if (L > 1) {
+    const HostCsr &hc = H.host.levels.back().A;
+    host_dense_inverse(hc, H.host.coarse_inv);
+    const int64_t nc = hc.nrows, cols = H.host.coarse_cols;
+    FNP_REQUIRE(cols == nc, FNP_ERR_STATE, "unexpected coarse inverse shape");
+    H.coarse_inv.upload(H.host.coarse_inv.data(), H.host.coarse_inv.size(), c.stream);
+    FNP_CUDA(cudaStreamSynchronize(c.stream));
+  }
+}
+
+}  // namespace fnp
+
+namespace fnp {
+
+// Host mirror of the level operators (values and Jacobi diagonals) after device-side refreshes.
+void amg_sync_host(Ctx &c, DevHierarchy &H) {
+  if (!H.host_vals_stale) return;
+  std::vector<double> buf;
+  for (size_t l = 0; l < H.levels.size(); ++l) {
+    DevCsr &A = H.levels[l].A();
+    HostCsr &h = H.host.levels[l].A;
+    buf.resize((size_t)dev_nvalues(A));
+    if (!buf.empty())
+      FNP_CUDA(cudaMemcpyAsync(buf.data(), dev_values(A), buf.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    FNP_CUDA(cudaStreamSynchronize(c.stream));
+    h.val.resize((size_t)h.nnz());
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < h.nnz(); ++k) h.val[(size_t)k] = buf[(size_t)dev_position(A, k)];
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < h.nrows; ++i) {
       double d = 0.0;
       for (int32_t k = h.rowptr[i]; k < h.rowptr[i + 1]; ++k)
@@ -110,23 +139,7 @@ void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs, const HostCsr &level0_h
       H.host.levels[l].dinv[(size_t)i] = d != 0.0 ? 1.0 / d : 0.0;
     }
   }
-  if (L > 1) {
-    const HostCsr &hc = H.host.levels.back().A;
-    host_dense_inverse(hc, H.host.coarse_inv);
-    const int64_t nc = hc.nrows, cols = H.host.coarse_cols;
-    FNP_REQUIRE(cols == nc, FNP_ERR_STATE, "unexpected coarse inverse shape");
-    if (bs == 1) {
-      H.coarse_inv.upload(H.host.coarse_inv.data(), H.host.coarse_inv.size(), c.stream);
-    } else {
-      std::vector<double> inv((size_t)H.coarse_n * H.coarse_cols, 0.0);
-      for (int64_t i = 0; i < nc; ++i)
-        for (int64_t j = 0; j < cols; ++j)
-          for (int b = 0; b < bs; ++b)
-            inv[(size_t)(i * bs + b) * H.coarse_cols + j * bs + b] = H.host.coarse_inv[(size_t)i * cols + j];
-      H.coarse_inv.upload(inv.data(), inv.size(), c.stream);
-    }
-    FNP_CUDA(cudaStreamSynchronize(c.stream));
-  }
+  H.host_vals_stale = false;
 }
 
 }  // namespace fnp

@@ -77,6 +77,7 @@ void Ctx::resolve_timers() {
       Timer &t = timers[p.name];
       t.ms += ms;
       t.calls += 1;
+      t.bytes += p.bytes;
     }
     event_pool.push_back(p.a);
     event_pool.push_back(p.b);
@@ -84,13 +85,13 @@ void Ctx::resolve_timers() {
   pending.clear();
 }
 
-StageTimer::StageTimer(Ctx &ctx, const char *nm, int level) : c(ctx) {
+StageTimer::StageTimer(Ctx &ctx, const char *nm, int level, double nbytes) : c(ctx), bytes(nbytes) {
   if (c.timers_on < level) return;
   name = nm;
   a = c.get_event();
   cudaEventRecord(a, c.stream);
 }
-StageTimer::StageTimer(Ctx &ctx, const std::string &nm, int level) : c(ctx) {
+StageTimer::StageTimer(Ctx &ctx, const std::string &nm, int level, double nbytes) : c(ctx), bytes(nbytes) {
   if (c.timers_on < level) return;
   name = nm;
   a = c.get_event();
@@ -100,7 +101,7 @@ StageTimer::~StageTimer() {
   if (!a) return;
   cudaEvent_t b = c.get_event();
   cudaEventRecord(b, c.stream);
-  c.pending.push_back({name, a, b});
+  c.pending.push_back({name, a, b, bytes});
   if (c.pending.size() > 200000) c.resolve_timers();
 }
 
@@ -217,8 +218,6 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
     else throw Error(FNP_ERR_OPTION, "option fnp_spmv_kernel: auto | csr | sell (takes effect at fnp_set_pattern)");
   } else if (name == "fnp_halo_p2p") {
     c.p2p = parse_int(name, v);
-  } else if (name == "fnp_reorder_nodes") {
-    c.reorder = std::max(0, (int)parse_int(name, v)) / 6 * 6;   // windows hold whole nodes for 2 and 3 components
   } else if (name == "fnp_sell_gather") {
     c.sell_gather = (int)parse_int(name, v);
     c.drop_graph();
@@ -240,261 +239,6 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
   } else {
     throw Error(FNP_ERR_OPTION, "unknown option '" + name + "'");
   }
-}
-
-// ---------------------------------------------------------------------------
-// operators
-// ---------------------------------------------------------------------------
-static void op_shape(const Ctx &c, int which, int64_t &nrows, int64_t &ncols) {
-  switch (which) {
-    case FNP_MAT_A00: case FNP_MAT_P00: nrows = c.n_u; ncols = c.n_u_global; break;
-    case FNP_MAT_A01: nrows = c.n_u; ncols = c.n_p_global; break;
-    case FNP_MAT_A10: nrows = c.n_p; ncols = c.n_u_global; break;
-    default: nrows = c.n_p; ncols = c.n_p_global; break;
-  }
-}
-
-double comm_allreduce(Ctx &c, double v, bool max_op);
-
-// Is the (sorted) pattern that of S (x) I_bs with interleaved components?  Rows bs*i+comp
-// must have equal length and columns bs*j+comp for the same nodes j.
-static bool kron_pattern(const HostCsr &h, int bs, int64_t col_shift_ok) {
-  if (bs < 2 || h.nrows == 0 || h.nrows % bs != 0 || h.ncols % bs != 0 || !col_shift_ok) return false;
-  const int64_t nn = h.nrows / bs;
-  bool ok = true;
-#pragma omp parallel for schedule(static) reduction(&& : ok)
-  for (int64_t i = 0; i < nn; ++i) {
-    const int32_t b0 = h.rowptr[bs * i], len = h.rowptr[bs * i + 1] - b0;
-    for (int comp = 0; comp < bs && ok; ++comp) {
-      const int32_t b = h.rowptr[bs * i + comp];
-      if (h.rowptr[bs * i + comp + 1] - b != len) { ok = false; break; }
-      for (int32_t k = 0; k < len; ++k)
-        if (h.col[b + k] % bs != comp || h.col[b + k] / bs != h.col[b0 + k] / bs) { ok = false; break; }
-    }
-  }
-  return ok;
-}
-
-static void set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t *colidx) {
-  FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must precede fnp_set_pattern");
-  FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT, FNP_ERR_ARG, "bad operator id");
-  FNP_REQUIRE(rowptr && (colidx || rowptr[0] == 0), FNP_ERR_ARG, "null pattern");
-  int64_t nrows, ncols;
-  op_shape(c, which, nrows, ncols);
-  HostCsr &h = c.hmat[which];
-  h.nrows = nrows;
-  h.ncols = ncols;
-  FNP_REQUIRE(rowptr[0] == 0, FNP_ERR_ARG, "rowptr[0] must be 0");
-  h.rowptr.assign(rowptr, rowptr + nrows + 1);
-  const int64_t nnz = h.rowptr[nrows];
-  FNP_REQUIRE(nnz >= 0, FNP_ERR_ARG, "negative nnz");
-  h.col.assign(colidx, colidx + nnz);
-  h.val.clear();
-  // sort every row by column, remember the permutation if anything moved
-  std::vector<int64_t> &perm = c.perm[which];
-  perm.clear();
-  bool sorted = true;
-  for (int64_t i = 0; i < nrows && sorted; ++i) {
-    FNP_REQUIRE(h.rowptr[i + 1] >= h.rowptr[i], FNP_ERR_ARG, "rowptr not monotone");
-    for (int32_t k = h.rowptr[i] + 1; k < h.rowptr[i + 1]; ++k)
-      if (h.col[k - 1] > h.col[k]) { sorted = false; break; }
-  }
-  if (!sorted) {
-    perm.resize(nnz);
-    std::iota(perm.begin(), perm.end(), (int64_t)0);
-    for (int64_t i = 0; i < nrows; ++i)
-      std::sort(perm.begin() + h.rowptr[i], perm.begin() + h.rowptr[i + 1],
-                [&](int64_t a, int64_t b) { return colidx[a] < colidx[b]; });
-    for (int64_t k = 0; k < nnz; ++k) h.col[k] = colidx[perm[k]];
-  }
-  for (int64_t i = 0; i < nrows; ++i) {
-    for (int32_t k = h.rowptr[i]; k < h.rowptr[i + 1]; ++k)
-      FNP_REQUIRE(h.col[k] >= 0 && h.col[k] < ncols, FNP_ERR_ARG, "column index out of range");
-  }
-  static const char *names[FNP_MAT_COUNT] = {"A00", "A01", "A10", "Ap", "Mp", "Kp", "P00"};
-  DevCsr &d = c.dmat[which];
-  // Kronecker detection for the velocity blocks (Picard/Oseen: the same scalar operator
-  // for every component).  Every rank must take the same decision.
-  int bs = 1;
-  if (c.kron && (which == FNP_MAT_A00 || which == FNP_MAT_P00)) {
-    for (int cand : {3, 2}) {
-      const bool aligned = c.u_begin % cand == 0 && c.n_u % cand == 0 && c.n_u_global % cand == 0;
-      double ok = kron_pattern(h, cand, aligned) ? 1.0 : 0.0;
-      ok = -comm_allreduce(c, -ok, true);          // min over ranks
-      if (ok > 0.5) { bs = cand; break; }
-    }
-  }
-  c.kron_bs[which] = bs;
-  c.kron_rowptr[which].clear();
-  if (bs > 1) {
-    // keep the scalar pattern (component 0 rows, node columns); remember the user's row
-    // pointers to pull and verify the values on every refresh
-    c.kron_rowptr[which] = h.rowptr;
-    HostCsr hs;
-    hs.nrows = h.nrows / bs;
-    hs.ncols = h.ncols / bs;
-    hs.rowptr.resize(hs.nrows + 1);
-    hs.rowptr[0] = 0;
-    for (int64_t i = 0; i < hs.nrows; ++i) hs.rowptr[i + 1] = hs.rowptr[i] + (h.rowptr[bs * i + 1] - h.rowptr[bs * i]);
-    hs.col.resize(hs.rowptr[hs.nrows]);
-    for (int64_t i = 0; i < hs.nrows; ++i)
-      for (int32_t k = 0; k < hs.rowptr[i + 1] - hs.rowptr[i]; ++k) hs.col[hs.rowptr[i] + k] = h.col[h.rowptr[bs * i] + k] / bs;
-    h = std::move(hs);
-  }
-  if (c.nranks == 1) {
-    csr_upload_pattern(c, d, h, names[which], -1, bs);
-  } else {
-    // multi-rank: the device copy uses local column numbering [owned | ghost]; the host
-    // copy keeps the global ids (the AMG set-up starts from them)
-    const bool u_cols = which == FNP_MAT_A00 || which == FNP_MAT_P00 || which == FNP_MAT_A10;
-    std::vector<int64_t> begins = u_cols ? c.u_begins : c.p_begins;
-    for (auto &b : begins) b /= bs;               // scalar (node) ownership in Kronecker mode
-    HostCsr loc = h;
-    std::shared_ptr<HaloPlan> plan = build_halo(c, loc, begins, nullptr);
-    const int64_t n_own_cols = begins[c.rank + 1] - begins[c.rank];
-    csr_upload_pattern(c, d, loc, names[which], (c.overlap || c.p2p) ? n_own_cols : -1, bs, n_own_cols);
-    d.halo = (plan && bs > 1) ? expand_plan(c, *plan, bs) : plan;
-    d.ncols_own = (int32_t)n_own_cols;
-    d.nghost = plan ? plan->nghost : 0;
-    c.local_cols[which] = std::move(loc.col);
-  }
-  c.have_pattern[which] = true;
-  c.have_values[which] = false;
-}
-
-static bool keeps_host_values(int which) {
-  return which == FNP_MAT_A00 || which == FNP_MAT_P00 || which == FNP_MAT_AP || which == FNP_MAT_A01;   // A01: Rp of PCDR
-}
-
-static void set_values(Ctx &c, int which, const double *values) {
-  FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT, FNP_ERR_ARG, "bad operator id");
-  FNP_REQUIRE(c.have_pattern[which], FNP_ERR_STATE, "fnp_set_values before fnp_set_pattern");
-  FNP_REQUIRE(values != nullptr || c.dmat[which].nnz == 0, FNP_ERR_ARG, "null values");
-  HostCsr &h = c.hmat[which];
-  const int bs = c.kron_bs[which];
-  const int64_t nnz_user = bs > 1 ? (int64_t)c.kron_rowptr[which].back() : h.nnz();
-  const std::vector<int64_t> &perm = c.perm[which];
-  const double *src = values;
-  std::vector<double> tmp, tmps;
-  if (!perm.empty()) {
-    tmp.resize(nnz_user);
-    for (int64_t k = 0; k < nnz_user; ++k) tmp[k] = values[perm[k]];
-    src = tmp.data();
-  }
-  if (bs > 1) {
-    // scalar values = component 0; the other components must carry the same numbers
-    const std::vector<int32_t> &rp = c.kron_rowptr[which];
-    tmps.resize(h.nnz());
-    bool ok = true;
-#pragma omp parallel for schedule(static) reduction(&& : ok)
-    for (int64_t i = 0; i < h.nrows; ++i) {
-      const int32_t len = h.rowptr[i + 1] - h.rowptr[i];
-      for (int32_t k = 0; k < len; ++k) {
-        const double v = src[rp[bs * i] + k];
-        tmps[h.rowptr[i] + k] = v;
-        for (int comp = 1; comp < bs; ++comp) {
-          const double w = src[rp[bs * i + comp] + k];
-          if (std::fabs(w - v) > 1e-13 * (std::fabs(v) + std::fabs(w))) ok = false;
-        }
-      }
-    }
-    FNP_REQUIRE(ok, FNP_ERR_STATE, "the velocity block has the pattern of S (x) I but its values differ between "
-                                   "components (Newton coupling / component-wise BCs?): set option fnp_kronecker 0 "
-                                   "before fnp_set_pattern");
-    src = tmps.data();
-  }
-  const int64_t nnz = h.nnz();
-  if (keeps_host_values(which)) {
-    h.val.assign(src, src + nnz);
-    src = h.val.data();
-  }
-  const bool want_dinv = which == FNP_MAT_MP || which == FNP_MAT_AP || which == FNP_MAT_A00 || which == FNP_MAT_P00;
-  if (c.nranks == 1) {
-    csr_set_values(c, c.dmat[which], h, src, want_dinv);
-  } else {
-    HostCsr view;                       // same rows, local column numbering (diagonal = row index)
-    view.nrows = h.nrows;
-    view.ncols = h.ncols;
-    view.rowptr = h.rowptr;
-    view.col = c.local_cols[which];
-    csr_set_values(c, c.dmat[which], view, src, want_dinv);
-  }
-  c.have_values[which] = true;
-  c.dirty[which] = true;
-}
-
-// opt-in internal numbering of the velocity dofs (Ctx::reorder) ------------------
-static bool u_rows(int which) { return which == FNP_MAT_A00 || which == FNP_MAT_P00 || which == FNP_MAT_A01; }
-static bool u_cols(int which) { return which == FNP_MAT_A00 || which == FNP_MAT_P00 || which == FNP_MAT_A10; }
-
-// Permuted copy of a user pattern: internal row i = user row u_perm[i] (velocity rows), columns
-// mapped through u_inv (velocity columns); c.rmap[which] maps internal entries to user entries.
-// FNP_MAT_A00 defines the permutation: dofs sorted by row length inside windows of c.reorder dofs
-// (stable, so the components of a node -- equal row lengths, adjacent -- stay interleaved).
-static void reorder_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t *colidx, std::vector<int32_t> &rp,
-                            std::vector<int32_t> &ci) {
-  c.rmap[which].clear();
-  if (!u_rows(which) && !u_cols(which)) return;
-  FNP_REQUIRE(c.nranks == 1, FNP_ERR_OPTION, "fnp_reorder_nodes is available on single-rank contexts only");
-  if (which == FNP_MAT_A00) {
-    FNP_REQUIRE(!c.have_pattern[FNP_MAT_A01] && !c.have_pattern[FNP_MAT_A10] && !c.have_pattern[FNP_MAT_P00] && c.mu_diag.empty() &&
-                    !c.have_is,
-                FNP_ERR_STATE, "with fnp_reorder_nodes, FNP_MAT_A00 must be set before the other velocity data");
-    const int64_t n = c.n_u;
-    c.u_perm.resize(n);
-    std::iota(c.u_perm.begin(), c.u_perm.end(), (int64_t)0);
-    for (int64_t w0 = 0; w0 < n; w0 += c.reorder) {
-      const int64_t w1 = std::min<int64_t>(n, w0 + c.reorder);
-      std::stable_sort(c.u_perm.begin() + w0, c.u_perm.begin() + w1, [&](int64_t a, int64_t b) {
-        return rowptr[a + 1] - rowptr[a] > rowptr[b + 1] - rowptr[b];
-      });
-    }
-    c.u_inv.resize(n);
-    for (int64_t i = 0; i < n; ++i) c.u_inv[c.u_perm[i]] = i;
-    c.d_u_perm.upload(c.u_perm.data(), (size_t)n, c.stream);
-    FNP_CUDA(cudaStreamSynchronize(c.stream));
-  }
-  FNP_REQUIRE(c.reordered(), FNP_ERR_STATE, "with fnp_reorder_nodes, FNP_MAT_A00 must be set before the other velocity data");
-  int64_t nrows, ncols;
-  op_shape(c, which, nrows, ncols);
-  FNP_REQUIRE(rowptr[0] == 0, FNP_ERR_ARG, "rowptr[0] must be 0");
-  for (int64_t i = 0; i < nrows; ++i) FNP_REQUIRE(rowptr[i + 1] >= rowptr[i], FNP_ERR_ARG, "rowptr not monotone");
-  const int64_t nnz = rowptr[nrows];
-  rp.assign(nrows + 1, 0);
-  ci.resize(nnz);
-  std::vector<int64_t> &map = c.rmap[which];
-  map.resize(nnz);
-  const bool pr = u_rows(which), pc = u_cols(which);
-  for (int64_t i = 0; i < nrows; ++i) {
-    const int64_t r = pr ? c.u_perm[i] : i;
-    rp[i + 1] = rp[i] + (rowptr[r + 1] - rowptr[r]);
-  }
-#pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < nrows; ++i) {
-    const int64_t r = pr ? c.u_perm[i] : i;
-    for (int32_t k = rowptr[r], q = rp[i]; k < rowptr[r + 1]; ++k, ++q) {
-      int32_t col = colidx[k];
-      if (pc && col >= 0 && col < ncols) col = (int32_t)c.u_inv[col];   // out-of-range ids are reported by set_pattern
-      ci[q] = col;
-      map[q] = k;
-    }
-  }
-}
-
-// user velocity vector (device) -> internal numbering, and back
-static const double *u_to_internal(Ctx &c, const double *user, DevBuf<double> &buf) {
-  if (!c.reordered()) return user;
-  buf.ensure((size_t)c.n_u);
-  vec_gather(c, c.n_u, c.d_u_perm.p, user, buf.p);
-  return buf.p;
-}
-static double *u_internal_out(Ctx &c, double *user) {
-  if (!c.reordered()) return user;
-  c.ro_out.ensure((size_t)c.n_u);
-  return c.ro_out.p;
-}
-static void u_to_user(Ctx &c, const double *internal, double *user) {
-  if (c.reordered()) vec_scatter(c, c.n_u, c.d_u_perm.p, internal, user);
 }
 
 // staging of host-pointer calls ---------------------------------------------
@@ -661,95 +405,15 @@ int fnp_set_layout(fnp_context *ctx, int64_t n_u_local, int64_t u_begin, int64_t
 int fnp_set_pattern(fnp_context *ctx, int which, const int32_t *rowptr, const int32_t *colidx) {
   FNP_API_BEGIN
   CTX(ctx);
-  FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must precede fnp_set_pattern");
-  FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT, FNP_ERR_ARG, "bad operator id");
-  FNP_REQUIRE(rowptr != nullptr, FNP_ERR_ARG, "null pattern");
-  std::vector<int32_t> re_rp, re_ci;
-  if (c.reorder > 0) {
-    reorder_pattern(c, which, rowptr, colidx, re_rp, re_ci);
-    if (!re_rp.empty()) {
-      rowptr = re_rp.data();
-      colidx = re_ci.data();
-    }
-  } else {
-    c.rmap[which].clear();
-  }
-  c.user_rowptr[which].clear();
-  c.user_col[which].clear();
-  c.pattern_pending[which] = false;
-  if (c.prune && (which == FNP_MAT_A00 || which == FNP_MAT_P00)) {
-    // DOLFIN stores the velocity block with the dense per-cell coupling of all components,
-    // explicit zeros included: the pattern is finalised at the first
-    // fnp_set_values, when the stored zeros are known and can be dropped
-    int64_t nrows, ncols;
-    op_shape(c, which, nrows, ncols);
-    FNP_REQUIRE(rowptr[0] == 0, FNP_ERR_ARG, "rowptr[0] must be 0");
-    for (int64_t i = 0; i < nrows; ++i) FNP_REQUIRE(rowptr[i + 1] >= rowptr[i], FNP_ERR_ARG, "rowptr not monotone");
-    c.user_rowptr[which].assign(rowptr, rowptr + nrows + 1);
-    c.user_col[which].assign(colidx, colidx + rowptr[nrows]);
-    c.user_nnz[which] = rowptr[nrows];
-    c.prune_mask[which].clear();
-    c.pattern_pending[which] = true;
-    c.have_pattern[which] = true;
-    c.have_values[which] = false;
-  } else {
-    set_pattern(c, which, rowptr, colidx);
-  }
+  ingest_set_pattern(c, which, rowptr, colidx);
   FNP_API_END
 }
 
 int fnp_set_values(fnp_context *ctx, int which, const double *values) {
   FNP_API_BEGIN
   CTX(ctx);
-  FNP_REQUIRE(which >= 0 && which < FNP_MAT_COUNT, FNP_ERR_ARG, "bad operator id");
-  FNP_REQUIRE(c.have_pattern[which], FNP_ERR_STATE, "fnp_set_values before fnp_set_pattern");
-  std::vector<double> re_vals;
-  if (!c.rmap[which].empty()) {
-    FNP_REQUIRE(values != nullptr, FNP_ERR_ARG, "null values");
-    const std::vector<int64_t> &map = c.rmap[which];
-    re_vals.resize(map.size());
-#pragma omp parallel for schedule(static)
-    for (int64_t k = 0; k < (int64_t)map.size(); ++k) re_vals[k] = values[map[k]];
-    values = re_vals.data();
-  }
-  const bool pruning = !c.user_rowptr[which].empty();
-  if (pruning) {
-    FNP_REQUIRE(values != nullptr, FNP_ERR_ARG, "null values");
-    const std::vector<int32_t> &rp = c.user_rowptr[which], &ci = c.user_col[which];
-    const int64_t nrows = (int64_t)rp.size() - 1, nnz = c.user_nnz[which];
-    const int64_t row0 = c.u_begin;                       // A00 / P00: square in the u numbering
-    std::vector<char> &keepmask = c.prune_mask[which];
-    // (re)build the pattern when it is still pending, or when an entry dropped earlier as a
-    // stored zero carries a value now (e.g. the convection term after a zero initial guess);
-    // the decision is collective because the pattern set-up is
-    double rebuild = c.pattern_pending[which] ? 1.0 : 0.0;
-    if (!c.pattern_pending[which])
-      for (int64_t k = 0; k < nnz; ++k)
-        if (!keepmask[k] && values[k] != 0.0) { rebuild = 1.0; break; }
-    rebuild = comm_allreduce(c, rebuild, true);
-    if (rebuild > 0.5) {
-      if (keepmask.size() != (size_t)nnz) keepmask.assign((size_t)nnz, 0);
-      std::vector<int32_t> prp(nrows + 1, 0), pci;
-      pci.reserve(nnz);
-      for (int64_t i = 0; i < nrows; ++i) {
-        for (int32_t k = rp[i]; k < rp[i + 1]; ++k) {
-          if (values[k] != 0.0 || ci[k] == row0 + i) keepmask[k] = 1;
-          if (keepmask[k]) pci.push_back(ci[k]);
-        }
-        prp[i + 1] = (int32_t)pci.size();
-      }
-      set_pattern(c, which, prp.data(), pci.data());
-      c.pattern_pending[which] = false;
-      c.is_setup = false;                                 // hierarchies / work space follow the new pattern
-    }
-    std::vector<double> packed;
-    packed.reserve(c.hmat[which].nnz() * (size_t)c.kron_bs[which]);
-    for (int64_t k = 0; k < nnz; ++k)
-      if (keepmask[k]) packed.push_back(values[k]);
-    set_values(c, which, packed.data());
-  } else {
-    set_values(c, which, values);
-  }
+  StageTimer t(c, "FENaPack: set_values");
+  ingest_set_values(c, which, values);
   FNP_API_END
 }
 
@@ -760,6 +424,7 @@ int fnp_set_bc(fnp_context *ctx, const int32_t *idx_local, const double *values,
   FNP_REQUIRE(n >= 0 && (n == 0 || (idx_local && values)), FNP_ERR_ARG, "bad BC arrays");
   for (int32_t i = 0; i < n; ++i)
     FNP_REQUIRE(idx_local[i] >= 0 && idx_local[i] < c.n_p, FNP_ERR_ARG, "BC index outside the local pressure range");
+  c.drop_graph();                       // the captured apply holds the BC buffers and their length
   c.nbc = n;
   c.bc_idx.upload(idx_local, (size_t)n, c.stream);
   c.bc_val.upload(values, (size_t)n, c.stream);
@@ -773,10 +438,6 @@ int fnp_set_mu_diag(fnp_context *ctx, const double *diag_local) {
   FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must precede fnp_set_mu_diag");
   FNP_REQUIRE(diag_local != nullptr || c.n_u == 0, FNP_ERR_ARG, "null diagonal");
   c.mu_diag.assign(diag_local, diag_local + c.n_u);
-  if (c.reorder > 0) {
-    FNP_REQUIRE(c.reordered(), FNP_ERR_STATE, "with fnp_reorder_nodes, FNP_MAT_A00 must be set before the other velocity data");
-    for (int64_t i = 0; i < c.n_u; ++i) c.mu_diag[i] = diag_local[c.u_perm[i]];
-  }
   c.mu_dirty = true;
   FNP_API_END
 }
@@ -811,13 +472,6 @@ int fnp_set_index_sets(fnp_context *ctx, const int64_t *is_u_local, const int64_
   check(is_p_local, c.n_p);
   c.is_u.upload(is_u_local, (size_t)c.n_u, c.stream);
   c.is_p.upload(is_p_local, (size_t)c.n_p, c.stream);
-  if (c.reorder > 0) {
-    // internal velocity dof i sits at monolithic position is_u[u_perm[i]]
-    FNP_REQUIRE(c.reordered(), FNP_ERR_STATE, "with fnp_reorder_nodes, FNP_MAT_A00 must be set before the other velocity data");
-    std::vector<int64_t> re((size_t)c.n_u);
-    for (int64_t i = 0; i < c.n_u; ++i) re[(size_t)i] = is_u_local[c.u_perm[i]];
-    c.d_is_u_re.upload(re.data(), re.size(), c.stream);
-  }
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   c.have_is = true;
   FNP_API_END
@@ -839,11 +493,7 @@ int fnp_spmv(fnp_context *ctx, int which, const double *x, double *y, int on_dev
   Staged s(c, on_device != 0);
   const double *dx = s.in(x, A.vec_cols());
   double *dy = s.out(y, A.vec_rows());
-  const bool rx = c.reordered() && which != FNP_MAT_RP && u_cols(which), ry = c.reordered() && which != FNP_MAT_RP && u_rows(which);
-  const double *ix = rx ? u_to_internal(c, dx, c.ro_in) : dx;
-  double *iy = ry ? u_internal_out(c, dy) : dy;
-  spmv_store(c, A, ix, iy);
-  if (ry) u_to_user(c, iy, dy);
+  spmv_store(c, A, dx, dy);
   s.finish();
   FNP_API_END
 }
@@ -890,9 +540,7 @@ int fnp_u_solve(fnp_context *ctx, const double *b, double *x, int on_device) {
   Staged s(c, on_device != 0);
   const double *db = s.in(b, c.n_u);
   double *dx = s.out(x, c.n_u);
-  double *ix = u_internal_out(c, dx);
-  u_solve(c, u_to_internal(c, db, c.ro_in), ix);
-  u_to_user(c, ix, dx);
+  u_solve(c, db, dx);
   s.finish();
   FNP_API_END
 }
@@ -919,9 +567,7 @@ int fnp_pc_apply(fnp_context *ctx, const double *x_u, const double *x_p, double 
   const double *dxp = s.in(x_p, c.n_p);
   double *dyu = s.out(y_u, c.n_u);
   double *dyp = s.out(y_p, c.n_p);
-  double *iyu = u_internal_out(c, dyu);
-  pc_apply(c, u_to_internal(c, dxu, c.ro_in), dxp, iyu, dyp);
-  u_to_user(c, iyu, dyu);
+  pc_apply(c, dxu, dxp, dyu, dyp);
   s.finish();
   check_p2p(c);
   FNP_API_END
@@ -940,24 +586,12 @@ int fnp_solve(fnp_context *ctx, const double *b_u, const double *b_p, double *x_
   bs.ensure((size_t)n);
   const cudaMemcpyKind in_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const cudaMemcpyKind out_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  if (c.reordered()) {
-    c.ro_in2.ensure((size_t)c.n_u);
-    FNP_CUDA(cudaMemcpyAsync(c.ro_in2.p, b_u, c.n_u * sizeof(double), in_kind, c.stream));
-    vec_gather(c, c.n_u, c.d_u_perm.p, c.ro_in2.p, bs.p);
-  } else {
-    FNP_CUDA(cudaMemcpyAsync(bs.p, b_u, c.n_u * sizeof(double), in_kind, c.stream));
-  }
+  FNP_CUDA(cudaMemcpyAsync(bs.p, b_u, c.n_u * sizeof(double), in_kind, c.stream));
   FNP_CUDA(cudaMemcpyAsync(bs.p + c.n_u, b_p, c.n_p * sizeof(double), in_kind, c.stream));
   int32_t its = 0, nap = 0;
   double rn = 0.0;
   solve_fgmres(c, bs.p, xs.p, &its, &rn, &nap);
-  const double *xu_src = xs.p;
-  if (c.reordered()) {
-    c.ro_in2.ensure((size_t)c.n_u);
-    vec_scatter(c, c.n_u, c.d_u_perm.p, xs.p, c.ro_in2.p);
-    xu_src = c.ro_in2.p;
-  }
-  FNP_CUDA(cudaMemcpyAsync(x_u, xu_src, c.n_u * sizeof(double), out_kind, c.stream));
+  FNP_CUDA(cudaMemcpyAsync(x_u, xs.p, c.n_u * sizeof(double), out_kind, c.stream));
   FNP_CUDA(cudaMemcpyAsync(x_p, xs.p + c.n_u, c.n_p * sizeof(double), out_kind, c.stream));
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   if (iterations) *iterations = its;
@@ -981,7 +615,7 @@ int fnp_solve_monolithic(fnp_context *ctx, const double *b, double *x, int on_de
     FNP_CUDA(cudaMemcpyAsync(mono.p, b, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     dmono = mono.p;
   }
-  const int64_t *isu = c.reordered() ? c.d_is_u_re.p : c.is_u.p;
+  const int64_t *isu = c.is_u.p;
   vec_gather(c, c.n_u, isu, dmono, bs.p);
   vec_gather(c, c.n_p, c.is_p.p, dmono, bs.p + c.n_u);
   int32_t its = 0, nap = 0;
@@ -1012,6 +646,7 @@ static DevHierarchy &hier(Ctx &c, int which) {
               "AMG hierarchies exist for FNP_MAT_AP, FNP_MAT_A00 and FNP_MAT_RP only");
   DevHierarchy &H = which == FNP_MAT_AP ? c.amg_ap : (which == FNP_MAT_RP ? c.amg_rp : c.amg_u);
   FNP_REQUIRE(H.built, FNP_ERR_STATE, "AMG hierarchy not built");
+  amg_sync_host(c, H);                  // device-side refreshes leave the host mirror behind
   return H;
 }
 
@@ -1077,10 +712,7 @@ int fnp_amg_vcycle(fnp_context *ctx, int which, const double *b, double *x, int 
   Staged s(c, on_device != 0);
   const double *db = s.in(b, n);
   double *dx = s.out(x, n);
-  const bool ru = c.reordered() && (which == FNP_MAT_A00 || which == FNP_MAT_P00);
-  double *ix = ru ? u_internal_out(c, dx) : dx;
-  amg_vcycle(c, H, ru ? u_to_internal(c, db, c.ro_in) : db, ix);
-  if (ru) u_to_user(c, ix, dx);
+  amg_vcycle(c, H, db, dx);
   s.finish();
   FNP_API_END
 }
@@ -1093,6 +725,35 @@ int fnp_get_timer(fnp_context *ctx, const char *name, double *ms, int64_t *calls
   if (ms) *ms = it == c.timers.end() ? 0.0 : it->second.ms;
   if (calls) *calls = it == c.timers.end() ? 0 : it->second.calls;
   FNP_API_END
+}
+
+int fnp_get_timer_bytes(fnp_context *ctx, const char *name, double *bytes) {
+  FNP_API_BEGIN
+  CTX(ctx);
+  c.resolve_timers();
+  auto it = c.timers.find(name ? name : "");
+  if (bytes) *bytes = it == c.timers.end() ? 0.0 : it->second.bytes;
+  FNP_API_END
+}
+
+int fnp_timer_names(fnp_context *ctx, char *out, int64_t capacity) {
+  if (!ctx) return FNP_ERR_ARG;
+  try {
+    ctx->c.resolve_timers();
+  } catch (...) {
+    return FNP_ERR_CUDA;
+  }
+  std::string all;
+  for (const auto &kv : ctx->c.timers) {
+    all += kv.first;
+    all += '\n';
+  }
+  if (out && capacity > 0) {
+    const size_t n = std::min<size_t>(all.size(), (size_t)capacity - 1);
+    std::memcpy(out, all.data(), n);
+    out[n] = '\0';
+  }
+  return (int)all.size();
 }
 
 int fnp_reset_timers(fnp_context *ctx) {

@@ -219,7 +219,8 @@ void multi_axpy_ptrs(Ctx &c, int64_t n, const double *const *Zptrs_dev, int nvec
 // v = w / sqrt(nrm2_dev[0])
 void vec_scale_inv_sqrt(Ctx &c, int64_t n, const double *nrm2_dev, const double *w, double *v);
 void dot(Ctx &c, int64_t n, const double *x, const double *y, double *out_dev);
-void dense_gemv(Ctx &c, int nrows, int ncols, const double *Minv, const double *b, double *x);
+// x = (Minv (x) I_bs) b: Minv dense row-major nrows x ncols (scalar), b and x with bs interleaved components
+void dense_gemv(Ctx &c, int nrows, int ncols, int bs, const double *Minv, const double *b, double *x);
 
 // ---------------------------------------------------------------------------
 // AMG
@@ -238,8 +239,9 @@ struct AmgParams {
                                      // coarsened/applied redundantly on every rank.  Off by default: +6 % at N=2
                                      // but slower (and 27 instead of 20 iterations) at N=8 with 300000
   double coarse_drop = 0.0;    // > 0: lump coarse entries below drop*sqrt(|a_ii||a_jj|) onto the diagonal
-  int refresh = 0;             // value refresh of an existing hierarchy: 0 rebuild on the host (or lag),
-                               // 1 frozen prolongators + Galerkin values recomputed on the device (amg_refresh.cu)
+  int refresh = 1;             // value refresh of an existing hierarchy: 0 rebuild on the host (or lag),
+                               // 1 frozen prolongators + Galerkin values recomputed on the device (amg_refresh.cu;
+                               // single-rank contexts, multi-rank ones fall back to 0)
 };
 
 struct HostLevel {
@@ -278,7 +280,7 @@ struct DevLevel {
 struct DevHierarchy {
   std::vector<DevLevel> levels;
   DevBuf<double> coarse_inv, coarse_gather;
-  int coarse_n = 0, coarse_cols = 0, coarse_maxloc = 0;
+  int coarse_n = 0, coarse_cols = 0, coarse_maxloc = 0, coarse_bs = 1;   // vector sizes (bs components per scalar row)
   bool serial = false;                 // replicated tail: applied without communication
   std::unique_ptr<DevHierarchy> tail;
   DevBuf<double> tail_gather, tail_b, tail_x, tail_bloc;
@@ -292,11 +294,13 @@ struct DevHierarchy {
   std::vector<DevCsr> refresh_W;
   std::vector<DevBuf<int32_t>> refresh_diag;
   bool refresh_built = false;
+  bool host_vals_stale = false;       // device-side refreshes since the host mirror was last synchronised
 };
 
 void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0, int bs);
 // new values on level 0 (same pattern): coarse operators recomputed on the device with frozen P
-void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs, const HostCsr &level0_host);
+void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs);
+void amg_sync_host(Ctx &c, DevHierarchy &H);     // host mirror of the level values after device-side refreshes
 // x = Vcycle(b), zero initial guess; b and x are level-0 sized device vectors (may not alias)
 void amg_vcycle(Ctx &c, DevHierarchy &H, const double *b, double *x);
 
@@ -323,10 +327,12 @@ struct InnerOpts {
 struct Timer {
   double ms = 0.0;
   int64_t calls = 0;
+  double bytes = 0.0;       // algorithmic bytes moved by the timed launches (0: not a single-kernel timer)
 };
 struct PendingTimer {
   std::string name;
   cudaEvent_t a, b;
+  double bytes;
 };
 
 struct Ctx {
@@ -364,7 +370,7 @@ struct Ctx {
   DevCsr rp;
   DevHierarchy amg_rp;
   int spmv_mode = 0;            // 0 auto (by row-length histogram), 1 CSR vector kernel always, 2 SELL always
-  int sell_gather = 15;         // SpMV kernel variant bits (kernels.cu): 1 wide gathers, 2 six CTAs/SM, 4 L2 prefetch, 8 wide epilogue (SELL);
+  int sell_gather = 95;         // SpMV kernel variant bits (kernels.cu): 1 wide gathers, 2 six CTAs/SM, 4 L2 prefetch, 8 wide epilogue (SELL);
                                 // 16 L2 prefetch in the CSR sub-warp kernel (experimental)
   int sell_sigma = 1024;        // SELL sorting window (rows)
   double sell_max_mean_row = 64.0;   // auto: operators with a longer mean row keep CSR + sub-warp per row
@@ -372,7 +378,6 @@ struct Ctx {
 
   // operators
   HostCsr hmat[FNP_MAT_COUNT];          // sorted host copies (pattern always; values for AMG operators)
-  std::vector<int64_t> perm[FNP_MAT_COUNT];   // user order -> sorted order (empty = identity)
   std::vector<int32_t> local_cols[FNP_MAT_COUNT];   // multi-rank: columns in local [owned | ghost] numbering
   int kron = 1;                                     // option fnp_kronecker: detect S (x) I_bs velocity blocks
   int prune = 1;                                    // option fnp_prune_zeros: drop stored zeros of A00/P00 at the first upload
@@ -380,6 +385,16 @@ struct Ctx {
   std::vector<int32_t> user_rowptr[FNP_MAT_COUNT], user_col[FNP_MAT_COUNT];
   std::vector<char> prune_mask[FNP_MAT_COUNT];      // per user entry: kept (1) or dropped as a stored zero (0)
   int64_t user_nnz[FNP_MAT_COUNT] = {};
+  // device-side value refresh (ingest.cu): stored entry -> position in the caller's value array.
+  // d_map: expanded (sorted, pruned, renumbered) entry -> user entry, empty when that is the identity;
+  // d_exp_rowptr: row pointers of the expanded pattern in Kronecker mode (the device operator holds the
+  // scalar pattern); d_dropped: user entries dropped as stored zeros (checked on every refresh)
+  DevBuf<int32_t> d_map[FNP_MAT_COUNT], d_exp_rowptr[FNP_MAT_COUNT], d_dropped[FNP_MAT_COUNT];
+  int64_t n_dropped[FNP_MAT_COUNT] = {};
+  bool host_vals_valid[FNP_MAT_COUNT] = {};         // hmat[w].val mirrors the device values (fetched lazily)
+  DevBuf<double> stage_vals;                         // staging of host value arrays (persistent)
+  DevBuf<int> d_flag;                                // error / decision word of the ingest kernels
+  int pattern_gen[FNP_MAT_COUNT] = {};               // bumped whenever the stored pattern of an operator is rebuilt
   int kron_bs[FNP_MAT_COUNT] = {1, 1, 1, 1, 1, 1, 1};
   std::vector<int32_t> kron_rowptr[FNP_MAT_COUNT];  // row pointers of the expanded (user) pattern, for value checks
   bool have_pattern[FNP_MAT_COUNT] = {};
@@ -395,6 +410,8 @@ struct Ctx {
 
   DevHierarchy amg_u, amg_ap;
   int amg_u_age = 0;            // value refreshes since the velocity hierarchy was last rebuilt
+  int amg_u_gen = -1;           // pattern generation of the velocity block the hierarchy was built for
+  int amg_u_which = -1;         // FNP_MAT_A00 or FNP_MAT_P00: the operator the velocity hierarchy belongs to
 
   // work space
   DevBuf<double> p_w[7];      // pressure-sized work vectors
@@ -422,17 +439,6 @@ struct Ctx {
   std::vector<DevBuf<double>> V, Z;
   DevBuf<double> kr_w, kr_x, kr_b;
   DevBuf<double> sol_x, sol_b, sol_m;   // staging of the user's b / x (split and monolithic layouts)
-  // Opt-in internal numbering of the velocity dofs (option fnp_reorder_nodes = window in dofs, 0 = off;
-  // single rank): dofs sorted by row length inside windows -- the SELL row order used as the vector
-  // numbering, so that a slice's rows AND gathered columns are consecutive (profiles/sell_gather_model.py).
-  // Operators are permuted at ingestion, user vectors at the entry / exit of every call.
-  int reorder = 0;
-  std::vector<int64_t> u_perm, u_inv;           // internal dof -> user dof, user dof -> internal dof
-  DevBuf<int64_t> d_u_perm, d_is_u_re;          // device copies: u_perm, is_u composed with u_perm
-  std::vector<int64_t> h_is_u;                  // host copy of the monolithic index set of the velocity dofs
-  std::vector<int64_t> rmap[FNP_MAT_COUNT];     // internal entry -> user entry of the operators that were permuted
-  DevBuf<double> ro_in, ro_in2, ro_out;         // permuted copies of user vectors
-  bool reordered() const { return !u_perm.empty(); }
   std::vector<double> res_hist;
 
   // timers
@@ -454,10 +460,16 @@ struct StageTimer {
   Ctx &c;
   std::string name;
   cudaEvent_t a = nullptr;
-  StageTimer(Ctx &ctx, const char *nm, int level = 1);
-  StageTimer(Ctx &ctx, const std::string &nm, int level);
+  double bytes = 0.0;
+  StageTimer(Ctx &ctx, const char *nm, int level = 1, double bytes = 0.0);
+  StageTimer(Ctx &ctx, const std::string &nm, int level, double bytes = 0.0);
   ~StageTimer();
 };
+
+// ingest.cu: pattern finalisation and the device-side value path of fnp_set_values
+void ingest_set_pattern(Ctx &c, int which, const int32_t *rowptr, const int32_t *colidx);
+void ingest_set_values(Ctx &c, int which, const double *values);
+void ensure_host_values(Ctx &c, int which);     // make hmat[which].val current (download from the device copy)
 
 // solver pieces (pcd.cu / gmres.cu)
 void setup_all(Ctx &c);

@@ -51,6 +51,15 @@ void solve_fgmres(Ctx &c, const double *b, double *x, int32_t *its_out, double *
   FNP_REQUIRE(m >= 1 && m <= 990, FNP_ERR_OPTION, "ksp_gmres_restart must be in [1, 990]");
   c.kr_w.ensure((size_t)n);
   c.red_out.ensure(1024);
+  {
+    // block partials of a full restart cycle, sized before the apply is captured: nothing that a
+    // captured kernel addresses may be reallocated later
+    const size_t need = (size_t)c.num_sms * 4 * (size_t)(m + 1 + 8);
+    if (c.red_partial.n < need) {
+      c.drop_graph();
+      c.red_partial.ensure(need);
+    }
+  }
   if (!c.pinned) {
     FNP_CUDA(cudaMallocHost(reinterpret_cast<void **>(&c.pinned), 1024 * sizeof(double)));
     c.pinned_n = 1024;

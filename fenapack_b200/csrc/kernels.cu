@@ -72,7 +72,7 @@ __device__ __forceinline__ void gather3_wide(const double *__restrict__ p, doubl
   a2 = odd ? hi.y : hi.x;
 }
 
-// PF (option fnp_sell_gather bit 16, experimental, off by default): lane 0 of every warp pulls the
+// PF (option fnp_sell_gather bit 16; round 2: A10 0.140 -> 0.119 ms isolated): lane 0 of every warp pulls the
 // contiguous (col, val) range of the warp's 32 / LANES rows into L2 with two bulk prefetches, as the
 // SELL kernel does for its slice (the ends are trimmed to 16-byte boundaries: a prefetch is a hint).
 template <int LANES, int BS, class Epi, bool PF>
@@ -145,10 +145,9 @@ constexpr int SELL_NARROW = 1;   // flag in bit 0 of a slice pointer (pointers a
 
 // Per-thread sums of one SELL row (entries k = 0 .. len-1 at stride 32).  WIDE selects the
 // 16-byte gathers (BS == 3 only); products and their order are the same in both variants.
-// PIPE (BS == 3, option bit 32, experimental): the column indices of the next group of four are
-// loaded before the gathers of the current one, taking the col -> gather dependency off the critical
-// path (ncu source view of the round-1 kernel: a third of the stall samples wait on the col loads).
-template <int BS, bool WIDE, bool PIPE>
+// (A variant that loaded the column indices of the next group of four ahead of the gathers was
+// measured slower in round 2 -- 0.177 / 0.205 ms against 0.170 ms on A00 -- and is gone.)
+template <int BS, bool WIDE>
 __device__ __forceinline__ void sell_row_sums(const int32_t *__restrict__ cp, const double *__restrict__ vp, int len,
                                               const double *__restrict__ x, const double *__restrict__ xg, int nown,
                                               double (&out)[BS]) {
@@ -156,27 +155,11 @@ __device__ __forceinline__ void sell_row_sums(const int32_t *__restrict__ cp, co
 #pragma unroll
   for (int b = 0; b < BS; ++b) s0[b] = s1[b] = 0.0;
   int k = 0;
-  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-  if (PIPE && len >= 4) {
-    c0 = __ldcs(cp + 0 * SELL_C);
-    c1 = __ldcs(cp + 1 * SELL_C);
-    c2 = __ldcs(cp + 2 * SELL_C);
-    c3 = __ldcs(cp + 3 * SELL_C);
-  }
   for (; k + 4 <= len; k += 4) {
-    if (!PIPE) {
-      c0 = __ldcs(cp + (k + 0) * SELL_C);
-      c1 = __ldcs(cp + (k + 1) * SELL_C);
-      c2 = __ldcs(cp + (k + 2) * SELL_C);
-      c3 = __ldcs(cp + (k + 3) * SELL_C);
-    }
-    int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-    if (PIPE && k + 8 <= len) {
-      n0 = __ldcs(cp + (k + 4) * SELL_C);
-      n1 = __ldcs(cp + (k + 5) * SELL_C);
-      n2 = __ldcs(cp + (k + 6) * SELL_C);
-      n3 = __ldcs(cp + (k + 7) * SELL_C);
-    }
+    const int c0 = __ldcs(cp + (k + 0) * SELL_C);
+    const int c1 = __ldcs(cp + (k + 1) * SELL_C);
+    const int c2 = __ldcs(cp + (k + 2) * SELL_C);
+    const int c3 = __ldcs(cp + (k + 3) * SELL_C);
     const double v0 = __ldcs(vp + (k + 0) * SELL_C), v1 = __ldcs(vp + (k + 1) * SELL_C);
     const double v2 = __ldcs(vp + (k + 2) * SELL_C), v3 = __ldcs(vp + (k + 3) * SELL_C);
     const double *p0 = gather_ptr<BS>(x, xg, nown, c0), *p1 = gather_ptr<BS>(x, xg, nown, c1);
@@ -202,12 +185,6 @@ __device__ __forceinline__ void sell_row_sums(const int32_t *__restrict__ cp, co
       s1[b] += v1 * x1[b];
       s0[b] += v2 * x2[b];
       s1[b] += v3 * x3[b];
-    }
-    if (PIPE) {
-      c0 = n0;
-      c1 = n1;
-      c2 = n2;
-      c3 = n3;
     }
   }
   for (; k < len; ++k) {
@@ -284,8 +261,8 @@ __device__ __forceinline__ void sell_prefetch(const int32_t *__restrict__ col, c
 }
 
 // VAR bits (option fnp_sell_gather): 1 16-byte gathers (BS == 3), 2 six CTAs per SM (40 registers),
-// 4 L2 bulk prefetch of the slice stream, 8 16-byte loads in the epilogue (BS == 3), 32 pipelined column
-// loads (BS == 3, experimental: only 45 and 47 are instantiated).
+// 4 L2 bulk prefetch of the slice stream, 8 16-byte loads in the epilogue (BS == 3), 64 default cache
+// policy instead of evict-first for operators that fit in L2 (BS == 1).
 // Measured on A00 = S (x) I_3 of the 64^3 cavity (profiles/r01_spmv_kernel_choice.md): 0.247 ms
 // with none, 0.178 ms with the prefetch alone, 0.170 ms with all.  A persistent variant (warps
 // striding over slices, next slice prefetched) was measured 2x slower and is not kept.
@@ -306,9 +283,9 @@ spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t 
   const int32_t *cp = col + base + lane;
   const double *vp = val + base + lane;
   if (BS == 1) {
-    // VAR bit 64 (experimental): operators that fit in L2 and are applied many times per PC apply
-    // (Ap, Mp, Kp and their coarse levels) load their stream with the default cache policy instead
-    // of evict-first, so that it stays resident between the applies
+    // VAR bit 64: operators that fit in L2 and are applied many times per PC apply (Ap, Mp, Kp and
+    // their coarse levels) load their stream with the default cache policy instead of evict-first,
+    // so that it stays resident between the applies (round 2, 64^3 cavity: Ap SpMV 11.0 -> 9.9 us)
     auto ldm_i = [](const int32_t *p) { return (VAR & 64) ? __ldg(p) : __ldcs(p); };
     auto ldm_d = [](const double *p) { return (VAR & 64) ? __ldg(p) : __ldcs(p); };
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -328,9 +305,9 @@ spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t 
   } else {
     double s[BS];
     if (BS == 3 && (VAR & 1) && !narrow)
-      sell_row_sums<BS, BS == 3, (VAR & 32) != 0>(cp, vp, len, x, xg, nown, s);
+      sell_row_sums<BS, BS == 3>(cp, vp, len, x, xg, nown, s);
     else
-      sell_row_sums<BS, false, false>(cp, vp, len, x, xg, nown, s);
+      sell_row_sums<BS, false>(cp, vp, len, x, xg, nown, s);
     if (row >= 0) {
       if constexpr (BS == 3 && (VAR & 8) != 0) {
         epilogue3(epi, row, s, !narrow);
@@ -355,22 +332,29 @@ static void sell_layout(const HostCsr &h, const std::vector<int32_t> &rows, std:
   const int64_t n = (int64_t)rows.size();
   const int64_t nsl = (n + SELL_C - 1) / SELL_C;
   perm.assign((size_t)nsl * SELL_C, -1);
-  for (int64_t w0 = 0; w0 < n; w0 += SELL_SIGMA) {
-    const int64_t w1 = std::min<int64_t>(n, w0 + SELL_SIGMA);
+  const int64_t nwin = (n + SELL_SIGMA - 1) / SELL_SIGMA;
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t w = 0; w < nwin; ++w) {
+    const int64_t w0 = w * SELL_SIGMA, w1 = std::min<int64_t>(n, w0 + SELL_SIGMA);
     for (int64_t i = w0; i < w1; ++i) perm[i] = rows[i];
     std::stable_sort(perm.begin() + w0, perm.begin() + w1, [&](int32_t a, int32_t b) {
       return h.rowptr[a + 1] - h.rowptr[a] > h.rowptr[b + 1] - h.rowptr[b];
     });
   }
   ptr.assign(nsl + 1, 0);
-  total = 0;
+  std::vector<int32_t> slen((size_t)nsl, 0);
+#pragma omp parallel for schedule(static)
   for (int64_t s = 0; s < nsl; ++s) {
     int32_t len = 0;
     for (int l = 0; l < SELL_C; ++l) {
       const int32_t r = perm[s * SELL_C + l];
       if (r >= 0) len = std::max(len, h.rowptr[r + 1] - h.rowptr[r]);
     }
-    total += (int64_t)len * SELL_C;
+    slen[s] = len;
+  }
+  total = 0;
+  for (int64_t s = 0; s < nsl; ++s) {
+    total += (int64_t)slen[s] * SELL_C;
     FNP_REQUIRE(total < (int64_t)INT32_MAX, FNP_ERR_ARG, "SELL layout exceeds 2^31 entries on one rank");
     ptr[s + 1] = (int32_t)total;
   }
@@ -406,12 +390,15 @@ static void sell_fill(const HostCsr &h, const std::vector<int32_t> &perm, const 
 static void build_sell(Ctx &c, DevCsr &A, const HostCsr &h, int64_t n_own_split, int64_t n_own_cols) {
   std::vector<int32_t> rows_a, rows_b;
   rows_a.reserve(h.nrows);
-  for (int64_t i = 0; i < h.nrows; ++i) {
-    bool ghost = false;
-    if (n_own_split >= 0)
-      for (int32_t k = h.rowptr[i]; k < h.rowptr[i + 1]; ++k)
-        if (h.col[k] >= n_own_split) { ghost = true; break; }
-    (ghost ? rows_b : rows_a).push_back((int32_t)i);
+  {
+    std::vector<char> ghost((size_t)h.nrows, 0);
+    if (n_own_split >= 0) {
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < h.nrows; ++i)
+        for (int32_t k = h.rowptr[i]; k < h.rowptr[i + 1]; ++k)
+          if (h.col[k] >= n_own_split) { ghost[i] = 1; break; }
+    }
+    for (int64_t i = 0; i < h.nrows; ++i) (ghost[i] ? rows_b : rows_a).push_back((int32_t)i);
   }
   std::vector<int32_t> perm_a, ptr_a, perm_b, ptr_b;
   int64_t tot_a = 0, tot_b = 0;
@@ -429,7 +416,8 @@ static void build_sell(Ctx &c, DevCsr &A, const HostCsr &h, int64_t n_own_split,
     const int32_t nown = n_own_cols >= 0 ? (int32_t)n_own_cols : (int32_t)h.ncols;
     const int32_t edge[4] = {0, nown - 1, nown, (int32_t)h.ncols - 1};
     auto flag = [&](std::vector<int32_t> &ptr, const std::vector<int32_t> &perm, int64_t off) {
-      for (size_t sl = 0; sl + 1 < ptr.size(); ++sl) {
+#pragma omp parallel for schedule(static)
+      for (int64_t sl = 0; sl < (int64_t)ptr.size() - 1; ++sl) {
         bool hit = false;
         for (int l = 0; l < SELL_C; ++l)     // first / last row: the epilogue's 16-byte loads
           hit = hit || perm[sl * SELL_C + l] == 0 || perm[sl * SELL_C + l] == (int32_t)h.nrows - 1;
@@ -527,7 +515,7 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
     xg = A.halo->current_ghost;
     nown = A.ncols_own;
   }
-  StageTimer kt(c, "spmv " + A.tag, 2);
+  StageTimer kt(c, "spmv " + A.tag, 2, A.spmv_bytes());
   if (A.sell) {
     auto launch = [&](int nsl, const int32_t *ptr, const int32_t *perm, int64_t off) {
       if (nsl <= 0) return;
@@ -535,12 +523,10 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
 #define FNP_SELL(V) \
   spmv_sell_kernel<BS, Epi, V><<<grid, threads, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, epi)
       if (BS == 3) {
-        switch (c.sell_gather & 47) {
+        switch (c.sell_gather & 15) {
           case 0: FNP_SELL(0); break;
           case 4: FNP_SELL(4); break;
           case 7: FNP_SELL(7); break;
-          case 45: FNP_SELL(45); break;      // pipelined column loads, registers uncapped
-          case 47: FNP_SELL(47); break;      // pipelined column loads, 6 CTAs/SM
           default: FNP_SELL(15); break;
         }
       } else {
@@ -730,6 +716,8 @@ static int red_blocks(const Ctx &c, int64_t n) { return blocks_for(c, n, RED_THR
 void multi_dot_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int nvec, const double *w, double *h_dev) {
   if (nvec <= 0) return;
   const int nblk = red_blocks(c, n);
+  // every batch of DOT_BATCH basis vectors re-reads w (SURVEY 8d counts the one-pass ideal 8N(j+2))
+  StageTimer kt(c, "multidot", 2, 8.0 * n * (nvec + (nvec + DOT_BATCH - 1) / DOT_BATCH));
   c.red_partial.ensure((size_t)nblk * (nvec + DOT_BATCH));
   dim3 grid(nblk, (nvec + DOT_BATCH - 1) / DOT_BATCH);
   multidot_kernel<<<grid, RED_THREADS, 0, c.stream>>>(n, Vptrs_dev, nvec, w, c.red_partial.p);
@@ -800,6 +788,7 @@ maxpy_norm_kernel(int64_t n, const double *const *__restrict__ V, int nvec, cons
 void multi_axpy_norm_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int nvec, const double *h_dev, double *w,
                           double *nrm2_dev) {
   const int nblk = red_blocks(c, n);
+  StageTimer kt(c, "maxpy+norm", 2, 8.0 * n * (nvec + 2));
   c.red_partial.ensure((size_t)nblk);
   maxpy_norm_kernel<<<nblk, RED_THREADS, nvec * sizeof(double), c.stream>>>(n, Vptrs_dev, nvec, h_dev, w, c.red_partial.p);
   FNP_LAUNCH_CHECK(c);
@@ -835,21 +824,39 @@ void vec_scale_inv_sqrt(Ctx &c, int64_t n, const double *nrm2_dev, const double 
   VEC_LAUNCH(scale_inv_sqrt_kernel, n, n, nrm2_dev, w, v);
 }
 
-// x = Minv b, Minv dense row-major n x n: one warp per row
+// x = (Minv (x) I_BS) b, Minv dense row-major nrows x n (scalar operator): one warp per scalar row,
+// the row of the inverse is read once for the BS interleaved components
+template <int BS>
 __global__ void __launch_bounds__(256)
 gemv_kernel(int nrows, int n, const double *__restrict__ M, const double *__restrict__ b, double *__restrict__ x) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= nrows) return;
-  double s = 0.0;
-  for (int k = lane; k < n; k += 32) s += M[(int64_t)row * n + k] * __ldg(b + k);
-  s = warp_sum(s);
-  if (lane == 0) x[row] = s;
+  double s[BS];
+#pragma unroll
+  for (int c = 0; c < BS; ++c) s[c] = 0.0;
+  for (int k = lane; k < n; k += 32) {
+    const double m = M[(int64_t)row * n + k];
+#pragma unroll
+    for (int c = 0; c < BS; ++c) s[c] += m * __ldg(b + (int64_t)BS * k + c);
+  }
+#pragma unroll
+  for (int c = 0; c < BS; ++c) {
+    const double v = warp_sum(s[c]);
+    if (lane == 0) x[(int64_t)BS * row + c] = v;
+  }
 }
 
-void dense_gemv(Ctx &c, int nrows, int ncols, const double *Minv, const double *b, double *x) {
+void dense_gemv(Ctx &c, int nrows, int ncols, int bs, const double *Minv, const double *b, double *x) {
   if (nrows <= 0) return;
-  gemv_kernel<<<(nrows * 32 + 255) / 256, 256, 0, c.stream>>>(nrows, ncols, Minv, b, x);
+  const int grid = (nrows * 32 + 255) / 256;
+  StageTimer kt(c, "gemv coarse", 2, 8.0 * nrows * (double)ncols + 8.0 * bs * (nrows + ncols));
+  switch (bs) {
+    case 1: gemv_kernel<1><<<grid, 256, 0, c.stream>>>(nrows, ncols, Minv, b, x); break;
+    case 2: gemv_kernel<2><<<grid, 256, 0, c.stream>>>(nrows, ncols, Minv, b, x); break;
+    case 3: gemv_kernel<3><<<grid, 256, 0, c.stream>>>(nrows, ncols, Minv, b, x); break;
+    default: throw Error(FNP_ERR_ARG, "unsupported block size");
+  }
   FNP_LAUNCH_CHECK(c);
 }
 

@@ -4,6 +4,8 @@
 // fenapack/field_split.py:54-57 selects.  The vector updates of the reference
 // (copy, axpy, scale -- one petsc4py call each) are folded into the epilogues
 // of the neighbouring SpMV-class kernels.
+#include <algorithm>
+
 #include "fnp_internal.cuh"
 
 namespace fnp {
@@ -233,13 +235,15 @@ static void build_amg(Ctx &c, int which, DevHierarchy &H, const AmgParams &p) {
   const int bs = c.kron_bs[which];
   std::vector<int64_t> begins = is_u ? c.u_begins : c.p_begins;
   for (auto &b : begins) b /= bs;              // Kronecker mode: the hierarchy is built on the scalar operator
+  ensure_host_values(c, which);                // the set-up runs on the host; values live on the device
+  c.drop_graph();                              // the captured apply addresses the old levels
   amg_build_host(c, c.hmat[which], begins, p, H.host);
   amg_upload(c, H, which == FNP_MAT_AP ? "Ap" : "A00", &c.dmat[which], bs);
+  H.host_vals_stale = false;
 }
 
 void setup_all(Ctx &c) {
   StageTimer t(c, "FENaPack: setup");
-  c.drop_graph();
   FNP_REQUIRE(c.have_layout, FNP_ERR_STATE, "fnp_set_layout must be called before fnp_setup");
   // pressure side is always needed; the velocity side only when the context owns the
   // whole block-triangular apply (n_u == 0: Schur-complement-only mode, the python-PC path)
@@ -250,26 +254,44 @@ void setup_all(Ctx &c) {
     for (int w : {(int)FNP_MAT_A00, (int)FNP_MAT_A01, (int)FNP_MAT_A10})
       FNP_REQUIRE(c.have_values[w], FNP_ERR_STATE, "fnp_setup: operator " + std::to_string(w) + " has no values");
   FNP_REQUIRE(c.variant >= 1 && c.variant <= 4, FNP_ERR_STATE, "PCD variant not set");
-  for (auto &b : c.p_w) b.ensure((size_t)c.n_p);
-  for (auto &b : c.u_w) b.ensure((size_t)c.n_u);
-  c.red_out.ensure(1024);
-  c.red_partial.ensure((size_t)c.num_sms * 4 * 200);     // sized once: no allocation inside the hot path
+  {
+    // work space: sized once; the captured apply addresses it, so a reallocation drops the graph
+    bool grow = c.red_out.n < 1024;
+    for (auto &b : c.p_w) grow = grow || b.n < (size_t)c.n_p;
+    for (auto &b : c.u_w) grow = grow || b.n < (size_t)c.n_u;
+    // block partials of the reductions: room for a full restart cycle (restart + 1 basis vectors and
+    // one batch of padding), so that nothing is reallocated inside the hot path or under a graph
+    const size_t red_need = (size_t)c.num_sms * 4 * (size_t)(std::max(c.restart, 192) + 1 + 8);
+    grow = grow || c.red_partial.n < red_need;
+    if (grow) {
+      c.drop_graph();
+      for (auto &b : c.p_w) b.ensure((size_t)c.n_p);
+      for (auto &b : c.u_w) b.ensure((size_t)c.n_u);
+      c.red_out.ensure(1024);
+      c.red_partial.ensure(red_need);
+    }
+  }
   const int uidx = c.velocity_pc_index();
   // AMG hierarchies (Ap: once; velocity block: whenever its values changed)
   if (c.opt_ap.pc == PC_AMG && (c.dirty[FNP_MAT_AP] || !c.amg_ap.built)) build_amg(c, FNP_MAT_AP, c.amg_ap, c.opt_ap.amg);
   if (have_u && c.opt_u.pc == PC_AMG && (c.dirty[uidx] || !c.amg_u.built)) {
-    // lagged refresh: level 0 aliases the context's operator and its Jacobi diagonal, so it
-    // always follows the new values; the coarse levels may be kept for `lag` refreshes
+    // value refresh of an existing hierarchy.  Level 0 aliases the context's operator and its
+    // Jacobi diagonal, so it always follows the new values; the coarse levels are
+    //   * recomputed on the device with frozen prolongators (pc_amg_refresh galerkin, the default), or
+    //   * kept for `lag` refreshes (pc_amg_lag), or
+    //   * rebuilt on the host.
+    // A pattern rebuild of the block (pruning found a new non-zero) invalidates the hierarchy.
     const bool same_shape = c.amg_u.built && !c.amg_u.levels.empty() && c.amg_u.levels[0].Ap == &c.dmat[uidx] &&
-                            c.amg_u.host.levels[0].A.nrows == c.dmat[uidx].nrows;
-    if (same_shape && c.opt_u.amg.refresh == 1 && c.nranks == 1) {
-      // frozen prolongators, Galerkin values recomputed on the device (amg_refresh.cu)
-      amg_refresh_device(c, c.amg_u, c.kron_bs[uidx], c.hmat[uidx]);
+                            c.amg_u_gen == c.pattern_gen[uidx] && c.amg_u_which == uidx;
+    if (same_shape && c.opt_u.amg.refresh == 1 && c.nranks == 1 && c.opt_u.amg.coarse_drop == 0.0) {
+      amg_refresh_device(c, c.amg_u, c.kron_bs[uidx]);
     } else if (same_shape && c.amg_u_age + 1 < c.opt_u.amg.lag) {
       ++c.amg_u_age;
     } else {
       build_amg(c, uidx, c.amg_u, c.opt_u.amg);
       c.amg_u_age = 0;
+      c.amg_u_gen = c.pattern_gen[uidx];
+      c.amg_u_which = uidx;
     }
   }
   if (c.variant >= 3) {
@@ -279,8 +301,11 @@ void setup_all(Ctx &c) {
     FNP_REQUIRE(c.have_values[FNP_MAT_A01] && (int64_t)c.mu_diag.size() == c.n_u, FNP_ERR_STATE,
                 "PCDR needs A01 (the discrete pressure gradient) and fnp_set_mu_diag");
     if (c.dirty[FNP_MAT_A01] || c.mu_dirty || !c.amg_rp.built) {
+      ensure_host_values(c, FNP_MAT_A01);
+      c.drop_graph();
       const HostCsr &Bt = c.hmat[FNP_MAT_A01];
       HostCsr S = Bt, B;                        // S = D^-1 Bt (rows scaled), B = Bt^T
+#pragma omp parallel for schedule(static)
       for (int64_t i = 0; i < S.nrows; ++i) {
         const double m = c.mu_diag[i];
         const double f = m != 0.0 ? 1.0 / m : 0.0;

@@ -99,19 +99,17 @@ int fnp_synchronize(fnp_context *ctx);
  *   <prefix>pc_amg_threshold, pc_amg_levels, pc_amg_coarse_size, pc_amg_smooth_steps,
  *   pc_amg_eig_ratio, pc_amg_prolongator_truncation, pc_amg_coarse_drop, pc_amg_replicate_size,
  *   pc_amg_lag (velocity block: rebuild the coarse levels at every lag-th refresh only),
- *   pc_amg_refresh rebuild|galerkin (velocity block, experimental: on a value refresh keep the prolongators and
- *   recompute the coarse operators on the device) for the prefixes fieldsplit_u_ and fieldsplit_p_PCD_Ap_
+ *   pc_amg_refresh galerkin|rebuild (velocity block; galerkin, the default on single-rank contexts: on a
+ *   value refresh keep the prolongators and recompute the coarse operators on the device; rebuild: redo
+ *   the host set-up) for the prefixes fieldsplit_u_ and fieldsplit_p_PCD_Ap_
  * "hypre"/"boomeramg"/"gamg" are accepted as aliases of amg (the smoothed-
  * aggregation hierarchy of this library).  Unknown names -> FNP_ERR_OPTION.
  * Library tuning knobs (prefix fnp_, not PETSc names): fnp_timers, fnp_cuda_graph, fnp_spmv_kernel
  * auto|csr|sell, fnp_sell_max_mean_row, fnp_sell_sigma (sorting window, before fnp_set_pattern),
  * fnp_sell_gather (bit mask: 1 16-byte gathers, 2 six CTAs/SM, 4 L2 bulk prefetch, 8 16-byte epilogue
- * loads, 16 L2 bulk prefetch in the CSR kernel (experimental), 32 pipelined column loads (experimental, as 45 or 47), 64 default instead of evict-first cache policy for
- * operators of at most 64 MB (experimental); default 15, results are bit-identical for every value), fnp_kronecker, fnp_prune_zeros,
- * fnp_halo_overlap, fnp_halo_p2p, fnp_reorder_nodes (experimental, single rank, before fnp_set_pattern:
- * window in dofs of a library-internal, row-length-sorted numbering of the velocity dofs; FNP_MAT_A00 must
- * then be the first velocity operator set; callers keep their own numbering in every call, only the AMG
- * introspection functions expose the internal one). */
+ * loads, 16 L2 bulk prefetch in the CSR kernel, 64 default instead of evict-first cache policy for
+ * operators of at most 64 MB; default 95 = all, results are bit-identical for every value),
+ * fnp_kronecker, fnp_prune_zeros, fnp_halo_overlap, fnp_halo_p2p. */
 int fnp_set_option(fnp_context *ctx, const char *name, const char *value);
 
 /* ---- operators -------------------------------------------------------- */
@@ -127,9 +125,12 @@ int fnp_set_layout(fnp_context *ctx, int64_t n_u_local, int64_t u_begin, int64_t
  * / the fieldsplit block extraction of PCSetUp_FieldSplit (field_split.py:90). */
 int fnp_set_pattern(fnp_context *ctx, int which, const int32_t *rowptr, const int32_t *colidx);
 
-/* Values for the pattern set before (host pointer, length nnz).  The value-only
- * refresh of the reference's MAT_REUSE_MATRIX path (field_split_backend.py:82-83,
- * 285-291): same pattern, new numbers, once per Newton step for A00/P00/KP. */
+/* Values for the pattern set before, length nnz, in the caller's entry order.  `values` may be a
+ * host pointer (pageable or pinned; copied to the device as it is) or a device pointer (used in
+ * place) -- the library asks the CUDA runtime which.  The value-only refresh of the reference's
+ * MAT_REUSE_MATRIX path (field_split_backend.py:82-83, 285-291): same pattern, new numbers, once
+ * per Newton step for A00/P00/KP.  All per-entry work (scatter into the stored format, Jacobi
+ * diagonal, Kronecker and pruning checks) runs on the device. */
 int fnp_set_values(fnp_context *ctx, int which, const double *values);
 
 /* PCD Dirichlet dofs in local pressure numbering and their values:
@@ -217,6 +218,13 @@ int fnp_amg_vcycle(fnp_context *ctx, int which, const double *b, double *x, int 
  * milliseconds and call counts since the last reset; enabled by
  * fnp_set_option(ctx, "fnp_timers", "1"). */
 int fnp_get_timer(fnp_context *ctx, const char *name, double *ms, int64_t *calls);
+/* Algorithmic bytes accumulated by the launches of a per-kernel timer
+ * (fnp_timers 2: "spmv <operator>", "multidot", "maxpy+norm", "gemv coarse"); 0 for stage timers
+ * that span several kernels.  bytes / ms is the achieved bandwidth the bench reports per stage. */
+int fnp_get_timer_bytes(fnp_context *ctx, const char *name, double *bytes);
+/* Names of all timers recorded since the last reset, newline separated, NUL terminated; returns the
+ * length needed (call with out = NULL to size the buffer). */
+int fnp_timer_names(fnp_context *ctx, char *out, int64_t capacity);
 int fnp_reset_timers(fnp_context *ctx);
 
 /* Number of CUDA kernel launches issued by this context since creation. */

@@ -24,12 +24,10 @@ def split(n, world, align=1):
     return b
 
 
-def main():
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    variant = sys.argv[1] if len(sys.argv) > 1 else "BRM1"
+def parity_check(rank, world, local, variant="BRM1", extra_options=None, p2p=None, repl=0):
+    """Row-partitioned library against the serial oracle on a small problem.  Collective over
+    torch.distributed (already initialised).  Returns the measured discrepancies; raises on a
+    violated tolerance."""
     prob, _ = problems.channel(12, 4, 6, variant=variant) if variant == "BRM1" else problems.lid_driven_cavity(8, dim=3, variant="BRM2")
     ub, pb = split(prob.n_u, world, 3), split(prob.n_p, world)
     u0, u1, p0, p1 = ub[rank], ub[rank + 1], pb[rank], pb[rank + 1]
@@ -42,11 +40,11 @@ def main():
     opts = dict(ITERATIVE_OPTIONS)
     opts["fieldsplit_p_pc_python_type"] = "fenapack.PCDPC_" + prob.variant
     opts["fieldsplit_p_PCD_Mp_ksp_chebyshev_eigenvalues"] = "%r, %r" % tuple(prob.cheb_bounds)
+    opts.update(extra_options or {})
     ctx.set_options(opts)
-    if os.environ.get("FNP_P2P"):          # exercise the peer-memory halo path as well
-        ctx.set_option("fnp_halo_p2p", os.environ["FNP_P2P"])
-    repl = int(os.environ.get("FNP_REPL", "0"))     # replicated coarse tail of the hierarchies
-    if repl:
+    if p2p is not None:                    # exercise the peer-memory halo path as well
+        ctx.set_option("fnp_halo_p2p", p2p)
+    if repl:                               # replicated coarse tail of the hierarchies
         ctx.set_option("fieldsplit_u_pc_amg_replicate_size", repl)
         ctx.set_option("fieldsplit_p_PCD_Ap_pc_amg_replicate_size", repl)
     ctx.set_layout(u1 - u0, p1 - p0, u0, prob.n_u, p0, prob.n_p)
@@ -61,38 +59,68 @@ def main():
     ctx.set_bc(prob.bc_idx[sel] - p0, prob.bc_val[sel])
     ctx.setup()
 
+    out = {}
     rng = np.random.default_rng(0)
     # distributed SpMV of every operator
+    worst = 0.0
     for which, (A, r0, r1) in mats.items():
         x = rng.standard_normal(A.shape[1])
         c0, c1 = (u0, u1) if A.shape[1] == prob.n_u else (p0, p1)
         y = ctx.spmv(which, x[c0:c1], r1 - r0)
-        assert relerr(y, (A @ x)[r0:r1]) <= 1e-12, ("spmv", which)
+        e = relerr(y, (A @ x)[r0:r1])
+        assert e <= 1e-12, ("spmv", which, e)
+        worst = max(worst, e)
+    out["spmv_relerr"] = worst
     # the preconditioner against the oracle with the same block-local hierarchy
     bs = ctx.block_size(capi.MAT_P00 if prob.P00 is not None else capi.MAT_A00)
     assert bs == 3, "the Picard velocity block should be recognised as S (x) I_3"
-    Hu = oracle_hierarchy_like_library(P00, bs=bs, blocks=ub, replicate_size=repl)
-    Hp = oamg.build_hierarchy(prob.Ap, blocks=pb, replicate_size=repl)
+    kw = {k[len("fieldsplit_u_pc_amg_"):]: int(v) for k, v in opts.items() if k == "fieldsplit_u_pc_amg_coarse_size"}
+    kwp = {k[len("fieldsplit_p_PCD_Ap_pc_amg_"):]: int(v) for k, v in opts.items() if k == "fieldsplit_p_PCD_Ap_pc_amg_coarse_size"}
+    Hu = oracle_hierarchy_like_library(P00, bs=bs, blocks=ub, replicate_size=repl, **kw)
+    Hp = oamg.build_hierarchy(prob.Ap, blocks=pb, replicate_size=repl, **kwp)
     pc = pa.PCDPreconditioner(prob, "iterative", amg_u=Hu, amg_p=Hp)
     b = rng.standard_normal(prob.n_p)
-    assert relerr(ctx.ap_solve(b[p0:p1]), pc.solve_Ap(b)[p0:p1]) <= 1e-9, "ap_solve"
+    out["ap_solve_relerr"] = relerr(ctx.ap_solve(b[p0:p1]), pc.solve_Ap(b)[p0:p1])
+    assert out["ap_solve_relerr"] <= 1e-9, "ap_solve"
     bu = rng.standard_normal(prob.n_u)
-    assert relerr(ctx.u_solve(bu[u0:u1]), pc.solve_A00(bu)[u0:u1]) <= 1e-9, "u_solve"
+    out["u_solve_relerr"] = relerr(ctx.u_solve(bu[u0:u1]), pc.solve_A00(bu)[u0:u1])
+    assert out["u_solve_relerr"] <= 1e-9, "u_solve"
     xu, xp = rng.standard_normal(prob.n_u), rng.standard_normal(prob.n_p)
     yu, yp = ctx.pc_apply(xu[u0:u1], xp[p0:p1])
     ru, rp = pc.apply_split(xu, xp)
-    assert relerr(yp, rp[p0:p1]) <= 1e-8 and relerr(yu, ru[u0:u1]) <= 1e-8, "pc_apply"
+    out["pc_apply_relerr"] = max(relerr(yp, rp[p0:p1]), relerr(yu, ru[u0:u1]))
+    assert out["pc_apply_relerr"] <= 1e-8, "pc_apply"
     # the outer solve
     A, rhs = prob.system_matrix(), prob.rhs()
     x_ref, its_ref, hist_ref, _ = pa.fgmres(A, pc, rhs, rtol=1e-6, restart=150)
     su, sp_, its, rn, nap = ctx.solve(prob.b_u[u0:u1], prob.b_p[p0:p1])
     assert abs(its - its_ref) <= 1, (its, its_ref)
     xs = np.concatenate([x_ref[:prob.n_u][u0:u1], x_ref[prob.n_u:][p0:p1]])
-    assert relerr(np.concatenate([su, sp_]), xs) <= 1e-5
+    out["solution_relerr"] = relerr(np.concatenate([su, sp_]), xs)
+    assert out["solution_relerr"] <= 1e-5
+    out.update({"its": int(its), "oracle_its": int(its_ref), "ndofs": int(prob.n_u + prob.n_p),
+                "problem": "channel 12x4x6 BRM1" if variant == "BRM1" else "cavity 8^3 BRM2"})
+    # worst case over the ranks (each rank checked its own rows)
+    t = torch.tensor([out[k] for k in ("spmv_relerr", "ap_solve_relerr", "u_solve_relerr", "pc_apply_relerr",
+                                       "solution_relerr")], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    for k, v in zip(("spmv_relerr", "ap_solve_relerr", "u_solve_relerr", "pc_apply_relerr", "solution_relerr"), t.tolist()):
+        out[k] = v
+    ctx.close()
+    return out
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    variant = sys.argv[1] if len(sys.argv) > 1 else "BRM1"
+    out = parity_check(rank, world, local, variant, p2p=os.environ.get("FNP_P2P") or None,
+                       repl=int(os.environ.get("FNP_REPL", "0")))
     dist.barrier()
     if rank == 0:
-        print(f"DIST OK world={world} variant={prob.variant} its={its} oracle_its={its_ref}")
-    ctx.close()
+        print(f"DIST OK world={world} variant={variant} its={out['its']} oracle_its={out['oracle_its']} {out}")
     dist.destroy_process_group()
 
 

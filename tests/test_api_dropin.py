@@ -89,14 +89,14 @@ def test_options_database_forwarding():
     Options.clear()
     o = Options("baz_")
     for k, v in (("ksp_gmres_restart", 150), ("fieldsplit_u_ksp_type", "richardson"), ("fieldsplit_u_pc_type", "hypre"),
-                 ("fieldsplit_u_mat_mumps_icntl_4", 2), ("ksp_monitor", ""), ("fnp_reorder_nodes", 3072),
+                 ("fieldsplit_u_mat_mumps_icntl_4", 2), ("ksp_monitor", ""), ("fnp_sell_sigma", 2048),
                  ("fieldsplit_u_pc_amg_refresh", "galerkin")):
         o.setValue(k, v)
     Options("other_").setValue("fnp_cuda_graph", 0)
     ksp = fp.PCDKSP()
     ksp.setOptionsPrefix("baz_")
     ksp.setFromOptions()
-    assert ksp._outer_opts == {"ksp_type": "gmres", "ksp_gmres_restart": "150", "fnp_reorder_nodes": "3072"}
+    assert ksp._outer_opts == {"ksp_type": "gmres", "ksp_gmres_restart": "150", "fnp_sell_sigma": "2048"}
     assert ksp._u_opts == {"fieldsplit_u_ksp_type": "richardson", "fieldsplit_u_pc_type": "hypre",
                            "fieldsplit_u_pc_amg_refresh": "galerkin"}
     Options.clear()
