@@ -15,7 +15,7 @@ namespace fnp {
 //   pass: c2 = 2 mu c1 - c0; omega = omegaprod c1/c2; p2 = (1-omega) p0 + omega p1 + omega s D^-1 (b - A p1)
 // `steps` = number of Jacobi applications.  Result: out = add + out_scale * p_last.
 void cheb_jacobi(Ctx &c, const DevCsr &A, const double *b, double emin, double emax, int steps, double out_scale,
-                 const double *add, double *out, double *w0, double *w1) {
+                 const double *add, double *out, double *w0, double *w1, bool p1_ready) {
   FNP_REQUIRE(A.has_dinv, FNP_ERR_STATE, "Chebyshev-Jacobi: operator has no Jacobi diagonal (fnp_setup missing)");
   FNP_REQUIRE(steps >= 1, FNP_ERR_ARG, "Chebyshev-Jacobi needs ksp_max_it >= 1");
   const int64_t n = A.vec_rows();
@@ -31,7 +31,7 @@ void cheb_jacobi(Ctx &c, const DevCsr &A, const double *b, double emin, double e
   double *buf[2] = {w0, w1};
   double *p0 = nullptr;
   double *p1 = buf[0];
-  vec_pointwise_scale(c, n, s, A.dinv.p, b, nullptr, p1);
+  if (!p1_ready) vec_pointwise_scale(c, n, s, A.dinv.p, b, nullptr, p1);     // else: written by the producer of b
   double c0 = 1.0, c1 = mu;
   for (int pass = 1; pass < steps; ++pass) {
     const double c2 = 2.0 * mu * c1 - c0;
@@ -77,6 +77,7 @@ void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0
   H.levels.clear();
   H.levels.resize(L);
   H.refresh_W.clear();          // plans of the device-side refresh belong to the old hierarchy
+  H.refresh_row0.clear();
   H.refresh_diag.clear();
   H.refresh_built = false;
   for (size_t l = 0; l < L; ++l) {
@@ -156,7 +157,7 @@ void amg_upload(Ctx &c, DevHierarchy &H, const std::string &name, DevCsr *level0
   H.built = true;
 }
 
-static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, double *x);
+static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, double *x, bool b_has_first_step = false);
 
 // coarse part replicated on every rank: all-gather the restricted residual, run the serial
 // tail V-cycle, keep the own slice of the correction (returned pointer)
@@ -169,7 +170,7 @@ static const double *tail_solve(Ctx &c, DevHierarchy &H, const double *b_loc) {
   return H.tail_x.p + H.tail_off;
 }
 
-static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, double *x) {
+static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, double *x, bool b_has_first_step) {
   DevLevel &L = H.levels[l];
   const bool last = l + 1 == H.levels.size();
   if (last && !H.tail) {
@@ -187,8 +188,21 @@ static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, dou
   }
   const AmgParams &p = H.params;
   const double emax = L.rho, emin = L.rho / p.eig_ratio;
+  // With >= 2 smoothing steps the first Chebyshev iterate s D^-1 b is a by-product of the kernel that
+  // produces b: the restriction of the level above (pre-smoothing) and the residual (post-smoothing)
+  // write it into the smoother's first buffer, which saves two launches per level.
+  const bool fuse = p.smooth_steps >= 2;
+  auto first_step = [&](DevLevel &lv) {
+    Jacobi1 j;
+    if (fuse) {
+      j.y2 = lv.w0.p;
+      j.d2 = lv.A().dinv.p;
+      j.s2 = cheb_first_step_scale(lv.rho / p.eig_ratio, lv.rho);
+    }
+    return j;
+  };
   // pre-smoothing from the zero initial guess
-  cheb_jacobi(c, L.A(), b, emin, emax, p.smooth_steps, 1.0, nullptr, x, L.w0.p, L.w1.p);
+  cheb_jacobi(c, L.A(), b, emin, emax, p.smooth_steps, 1.0, nullptr, x, L.w0.p, L.w1.p, fuse && b_has_first_step);
   // r = b - A x ; b_c = R r
   spmv_axpby(c, L.A(), x, -1.0, 1.0, b, L.r.p);
   const double *xc;
@@ -197,15 +211,16 @@ static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, dou
     xc = tail_solve(c, H, H.tail_bloc.p);
   } else {
     DevLevel &C = H.levels[l + 1];
-    spmv_store(c, L.R, L.r.p, C.b.p);
-    vcycle_level(c, H, l + 1, C.b.p, C.x.p);
+    const bool c_smooths = !(l + 2 == H.levels.size() && !H.tail);      // the coarsest level is solved, not smoothed
+    spmv_store(c, L.R, L.r.p, C.b.p, c_smooths ? first_step(C) : Jacobi1());
+    vcycle_level(c, H, l + 1, C.b.p, C.x.p, c_smooths && fuse);
     xc = C.x.p;
   }
   // x += P x_c
   spmv_axpby(c, L.P, xc, 1.0, 1.0, x, x);
   // post-smoothing on the correction equation: x += cheb(A, b - A x)
-  spmv_axpby(c, L.A(), x, -1.0, 1.0, b, L.r.p);
-  cheb_jacobi(c, L.A(), L.r.p, emin, emax, p.smooth_steps, 1.0, x, x, L.w0.p, L.w1.p);
+  spmv_axpby(c, L.A(), x, -1.0, 1.0, b, L.r.p, first_step(L));
+  cheb_jacobi(c, L.A(), L.r.p, emin, emax, p.smooth_steps, 1.0, x, x, L.w0.p, L.w1.p, fuse);
 }
 
 void amg_vcycle(Ctx &c, DevHierarchy &H, const double *b, double *x) {

@@ -11,6 +11,8 @@
 // Option pc_amg_refresh galerkin (the default on single-rank contexts); covered on the GPU by
 // tests/test_gpu_parity.py::test_device_side_galerkin_refresh and the refresh tests of
 // tests/test_api_dropin.py, host plan logic by tests/test_host_logic.py.
+#include <algorithm>
+
 #include "fnp_internal.cuh"
 #include "galerkin_plan.hpp"
 
@@ -34,8 +36,10 @@ __global__ void refresh_dinv_kernel(int64_t n, const int32_t *__restrict__ diagp
 static void build_plans(Ctx &c, DevHierarchy &H) {
   const size_t L = H.levels.size();
   H.refresh_W.clear();
+  H.refresh_row0.clear();
   H.refresh_diag.clear();
   H.refresh_W.resize(L - 1);
+  H.refresh_row0.resize(L - 1);
   H.refresh_diag.resize(L - 1);
   for (size_t l = 0; l + 1 < L; ++l) {
     const HostLevel &hf = H.host.levels[l], &hc = H.host.levels[l + 1];
@@ -46,27 +50,56 @@ static void build_plans(Ctx &c, DevHierarchy &H) {
       throw Error(FNP_ERR_STATE, e.what());
     }
     DevCsr &Af = H.levels[l].A(), &Ac = H.levels[l + 1].A();
-    FNP_REQUIRE(plan.terms() < (int64_t)INT32_MAX, FNP_ERR_ARG, "Galerkin refresh plan exceeds 2^31 terms");
-    // W re-indexed: row = device position of the coarse entry, column = device position of the fine entry
-    HostCsr W;
-    W.nrows = dev_nvalues(Ac);
-    W.ncols = dev_nvalues(Af);
-    W.rowptr.assign((size_t)W.nrows + 1, 0);
-    const int64_t nq = hc.A.nnz();
-    for (int64_t q = 0; q < nq; ++q) W.rowptr[(size_t)dev_position(Ac, q) + 1] = (int32_t)(plan.ptr[q + 1] - plan.ptr[q]);
-    for (int64_t r = 0; r < W.nrows; ++r) W.rowptr[(size_t)r + 1] += W.rowptr[(size_t)r];
-    W.col.resize((size_t)plan.terms());
-    W.val.resize((size_t)plan.terms());
+    // W re-indexed: row = device position of the coarse entry, column = device position of the fine
+    // entry.  Stored in row chunks of at most ~2^30 terms (32-bit entry offsets on the device): level 0
+    // of the 128^3 cavity has 1.7e9 terms.
+    const int64_t wrows = dev_nvalues(Ac), nq = hc.A.nnz();
+    std::vector<int64_t> cnt((size_t)wrows + 1, 0);            // terms per W row, then offsets
+    for (int64_t q = 0; q < nq; ++q) cnt[(size_t)dev_position(Ac, q) + 1] = plan.ptr[q + 1] - plan.ptr[q];
+    for (int64_t r = 0; r < wrows; ++r) cnt[(size_t)r + 1] += cnt[(size_t)r];
+    std::vector<int64_t> row_of_q((size_t)nq);
 #pragma omp parallel for schedule(static)
-    for (int64_t q = 0; q < nq; ++q) {
-      int64_t dst = W.rowptr[(size_t)dev_position(Ac, q)];
-      for (int64_t t = plan.ptr[q]; t < plan.ptr[q + 1]; ++t, ++dst) {
-        W.col[(size_t)dst] = (int32_t)dev_position(Af, plan.src[(size_t)t]);
-        W.val[(size_t)dst] = plan.coef[(size_t)t];
-      }
+    for (int64_t q = 0; q < nq; ++q) row_of_q[(size_t)q] = dev_position(Ac, q);
+    const int64_t LIMIT = c.refresh_chunk_terms;
+    std::vector<int64_t> cuts{0};
+    while (cuts.back() < wrows) {
+      const int64_t r0 = cuts.back();
+      // largest r1 with terms(r0, r1) <= LIMIT (at least one row)
+      int64_t r1 = std::upper_bound(cnt.begin() + r0 + 1, cnt.end(), cnt[(size_t)r0] + LIMIT) - cnt.begin() - 1;
+      r1 = std::max(r1, r0 + 1);
+      cuts.push_back(std::min(r1, wrows));
     }
-    csr_upload_pattern(c, H.refresh_W[l], W, "refresh/W" + std::to_string(l));
-    csr_set_values(c, H.refresh_W[l], W, W.val.data(), false);
+    const size_t nchunk = cuts.size() - 1;
+    H.refresh_W[l].resize(nchunk);
+    H.refresh_row0[l].assign(cuts.begin(), cuts.end() - 1);
+    for (size_t ch = 0; ch < nchunk; ++ch) {
+      const int64_t r0 = cuts[ch], r1 = cuts[ch + 1], t0 = cnt[(size_t)r0];
+      HostCsr W;
+      W.nrows = r1 - r0;
+      W.ncols = dev_nvalues(Af);
+      W.rowptr.resize((size_t)W.nrows + 1);
+#pragma omp parallel for schedule(static)
+      for (int64_t r = r0; r <= r1; ++r) W.rowptr[(size_t)(r - r0)] = (int32_t)(cnt[(size_t)r] - t0);
+      const int64_t terms = cnt[(size_t)r1] - t0;
+      FNP_REQUIRE(terms < (int64_t)INT32_MAX, FNP_ERR_ARG, "Galerkin refresh plan: one coarse entry with more than 2^31 terms");
+      W.col.resize((size_t)terms);
+      W.val.resize((size_t)terms);
+#pragma omp parallel for schedule(static)
+      for (int64_t q = 0; q < nq; ++q) {
+        const int64_t r = row_of_q[(size_t)q];
+        if (r < r0 || r >= r1) continue;
+        int64_t dst = cnt[(size_t)r] - t0;
+        for (int64_t t = plan.ptr[q]; t < plan.ptr[q + 1]; ++t, ++dst) {
+          W.col[(size_t)dst] = (int32_t)dev_position(Af, plan.src[(size_t)t]);
+          W.val[(size_t)dst] = plan.coef[(size_t)t];
+        }
+      }
+      DevCsr &Wd = H.refresh_W[l][ch];
+      csr_upload_pattern(c, Wd, W, "refresh/W" + std::to_string(l));
+      csr_set_values(c, Wd, W, W.val.data(), false);
+      Wd.sell_pos.clear();
+      Wd.sell_pos.shrink_to_fit();                  // the plan is never refreshed itself
+    }
     std::vector<int32_t> dp((size_t)hc.A.nrows, -1);
     for (int64_t i = 0; i < hc.A.nrows; ++i)
       for (int32_t k = hc.A.rowptr[i]; k < hc.A.rowptr[i + 1]; ++k)
@@ -86,7 +119,8 @@ void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs) {
   if (L > 1 && !H.refresh_built) build_plans(c, H);
   for (size_t l = 0; l + 1 < L; ++l) {
     DevCsr &Af = H.levels[l].A(), &Ac = H.levels[l + 1].A();
-    spmv_store(c, H.refresh_W[l], dev_values(Af), dev_values(Ac));
+    for (size_t ch = 0; ch < H.refresh_W[l].size(); ++ch)
+      spmv_store(c, H.refresh_W[l][ch], dev_values(Af), dev_values(Ac) + H.refresh_row0[l][ch]);
     const int64_t n = Ac.nrows;
     refresh_dinv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(n, H.refresh_diag[l].p, dev_values(Ac), Ac.dinv.p, bs);
     c.launches++;

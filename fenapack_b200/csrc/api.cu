@@ -52,6 +52,7 @@ Ctx::~Ctx() {
   if (pinned) cudaFreeHost(pinned);
   for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : event_pool) cudaEventDestroy(e);
+  for (auto e : ev_iter) cudaEventDestroy(e);
   if (ev_tic) cudaEventDestroy(ev_tic);
   if (ev_toc) cudaEventDestroy(ev_toc);
   if (own_stream && stream) cudaStreamDestroy(stream);
@@ -221,6 +222,16 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
   } else if (name == "fnp_sell_gather") {
     c.sell_gather = (int)parse_int(name, v);
     c.drop_graph();
+  } else if (name == "fnp_refresh_chunk_terms") {
+    c.refresh_chunk_terms = std::max<int64_t>(1, (int64_t)parse_real(name, v));
+  } else if (name == "fnp_sell_warps_rows") {
+    c.sell_warps_rows = (int64_t)parse_real(name, v);
+  } else if (name == "fnp_gmres_sync") {
+    c.gmres_sync = parse_int(name, v);
+  } else if (name == "fnp_sell_warps") {
+    c.sell_warps = (int)parse_int(name, v);
+    FNP_REQUIRE(c.sell_warps == 0 || c.sell_warps == 1 || c.sell_warps == 2 || c.sell_warps == 4 || c.sell_warps == 8,
+                FNP_ERR_OPTION, "fnp_sell_warps: 0 (auto), 1, 2, 4 or 8 (takes effect at fnp_set_pattern / fnp_setup)");
   } else if (name == "fnp_sell_sigma") {
     c.sell_sigma = std::max(32, (int)parse_int(name, v) / 32 * 32);
   } else if (name == "fnp_sell_max_mean_row") {

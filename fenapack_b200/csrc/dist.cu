@@ -29,8 +29,12 @@ __global__ void pack_kernel(int32_t n, const int32_t *__restrict__ idx, const do
 __global__ void __launch_bounds__(256)
 p2p_send_kernel(int32_t nsend, const int32_t *__restrict__ idx, const double *__restrict__ x, int nranks,
                 const int *__restrict__ send_off, const int *__restrict__ send_cnt, double *const *__restrict__ peer_dst,
-                const long long *__restrict__ peer_stride, unsigned long long *const *__restrict__ peer_flag, int slot,
-                unsigned long long seq, unsigned int *counter) {
+                const long long *__restrict__ peer_stride, unsigned long long *const *__restrict__ peer_flag,
+                unsigned long long *seq_dev, unsigned int *counter) {
+  // the sequence number of THIS exchange; *seq_dev is advanced by the last block to finish, i.e.
+  // after every block of the launch has read it
+  const unsigned long long seq = *((volatile unsigned long long *)seq_dev) + 1ull;
+  const int slot = (int)(seq & 1ull);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nsend) {
     int q = 0;
@@ -47,6 +51,7 @@ p2p_send_kernel(int32_t nsend, const int32_t *__restrict__ idx, const double *__
     const unsigned int done = atomicAdd(counter, 1u);
     if (done == gridDim.x - 1) {
       *counter = 0;
+      *((volatile unsigned long long *)seq_dev) = seq;
       __threadfence_system();
       for (int q = 0; q < nranks; ++q)
         if (send_cnt[q] > 0) *((volatile unsigned long long *)peer_flag[q]) = seq;
@@ -54,16 +59,16 @@ p2p_send_kernel(int32_t nsend, const int32_t *__restrict__ idx, const double *__
   }
 }
 
-// wait: one thread per peer spins on the local flag word (bounded: ~4 s, then the error
-// flag is raised instead of hanging the GPU)
-__global__ void p2p_wait_kernel(int nranks, const int *__restrict__ recv_cnt, const unsigned long long *flags,
-                                unsigned long long seq, int *err) {
+// stand-alone wait (host-side consumers): one thread per peer spins on the local flag word
+// (bounded: ~4 s, then the error flag is raised instead of hanging the GPU)
+__global__ void p2p_wait_kernel(const HaloWaitDev *__restrict__ hw) {
   const int q = threadIdx.x;
-  if (q >= nranks || recv_cnt[q] == 0) return;
+  if (q >= hw->nranks || hw->recv_cnt[q] == 0) return;
+  const unsigned long long seq = *hw->seq;
   const long long t0 = clock64();
-  while (*((volatile const unsigned long long *)(flags + q)) < seq) {
+  while (*((volatile const unsigned long long *)(hw->flags + q)) < seq) {
     if (clock64() - t0 > 8000000000ll) {
-      *err = 1;
+      *hw->err = 1;
       return;
     }
   }
@@ -76,16 +81,14 @@ HaloPlan::~HaloPlan() {
 
 void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own, cudaStream_t stream, ncclComm_t comm) {
   if (h.p2p) {
-    const unsigned long long seq = ++h.seq;
-    const int slot = (int)(seq & 1ull);
     if (h.nsend > 0) {
       p2p_send_kernel<<<(h.nsend + 255) / 256, 256, 0, stream>>>(h.nsend, h.send_idx.p, x_own, c.nranks, h.d_send_off.p,
                                                                   h.d_send_cnt.p, h.d_peer_dst.p, h.d_peer_stride.p,
-                                                                  h.d_peer_flag.p, slot, seq, h.d_counter.p);
+                                                                  h.d_peer_flag.p, h.d_seq.p, h.d_counter.p);
       c.launches++;
       FNP_CUDA(cudaPeekAtLastError());
     }
-    h.current_ghost = h.arena.p + (size_t)slot * h.nghost;
+    h.current_ghost = nullptr;        // the slot follows the device-resident sequence number
     return;
   }
   if (h.nsend > 0) {
@@ -107,10 +110,17 @@ void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own, cudaStream_t stream
 
 void halo_wait(Ctx &c, HaloPlan &h, cudaStream_t stream) {
   if (!h.p2p || h.nghost == 0) return;
-  p2p_wait_kernel<<<1, 32, 0, stream>>>(c.nranks, h.d_recv_cnt.p, reinterpret_cast<const unsigned long long *>(h.arena.p + 2 * (size_t)h.nghost),
-                                        h.seq, c.p2p_err.p);
+  p2p_wait_kernel<<<1, 32, 0, stream>>>(h.d_wait.p);
   c.launches++;
   FNP_CUDA(cudaPeekAtLastError());
+}
+
+const double *halo_ghost_after_wait(Ctx &c, HaloPlan &h) {
+  if (!h.p2p) return h.current_ghost;
+  unsigned long long seq = 0;
+  FNP_CUDA(cudaMemcpyAsync(&seq, h.d_seq.p, sizeof(seq), cudaMemcpyDeviceToHost, c.stream));
+  FNP_CUDA(cudaStreamSynchronize(c.stream));
+  return h.arena.p + (size_t)(seq & 1ull) * (size_t)h.nghost;
 }
 
 // cudaIpcGetMemHandle describes the BASE allocation a pointer lives in (cudaMalloc may
@@ -205,6 +215,17 @@ void halo_enable_p2p(Ctx &c, HaloPlan &h) {
   h.d_recv_cnt.upload(h.recv_count.data(), R, c.stream);
   h.d_counter.alloc(1);
   h.d_counter.zero(c.stream);
+  h.d_seq.alloc(1);
+  h.d_seq.zero(c.stream);
+  HaloWaitDev hw;
+  hw.arena = h.arena.p;
+  hw.seq = h.d_seq.p;
+  hw.flags = reinterpret_cast<const unsigned long long *>(h.arena.p + 2 * (size_t)h.nghost);
+  hw.recv_cnt = h.d_recv_cnt.p;
+  hw.err = c.p2p_err.p;
+  hw.nranks = R;
+  hw.nghost = h.nghost;
+  h.d_wait.upload(&hw, 1, c.stream);
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   // nobody may start sending before every rank has zeroed its flags and mapped its peers
   comm_allreduce(c, 0.0, false);
@@ -376,7 +397,8 @@ std::vector<double> halo_exchange_host(Ctx &c, HaloPlan &plan, const std::vector
   halo_exchange(c, plan, d.p, c.stream, c.comm);
   halo_wait(c, plan, c.stream);
   std::vector<double> g((size_t)plan.nghost);
-  if (plan.nghost) FNP_CUDA(cudaMemcpyAsync(g.data(), plan.current_ghost, g.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  const double *ghost = halo_ghost_after_wait(c, plan);
+  if (plan.nghost) FNP_CUDA(cudaMemcpyAsync(g.data(), ghost, g.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   FNP_CUDA(cudaStreamSynchronize(c.stream));
   return g;
 }

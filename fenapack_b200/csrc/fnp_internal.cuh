@@ -112,6 +112,17 @@ struct Ctx;
 // x each peer needs (send_idx, grouped by peer) and where the entries received from
 // each peer land in the ghost buffer (ghost columns are sorted by global id, hence
 // grouped by owner).
+// what a ghost-consuming kernel needs to wait for a peer-memory exchange (lives in device memory)
+struct HaloWaitDev {
+  const double *arena;                  // [2 ghost slots | flags]
+  const unsigned long long *seq;        // exchanges posted so far on this plan
+  const unsigned long long *flags;      // one per rank: last sequence number that rank delivered
+  const int *recv_cnt;                  // per rank: entries expected (0: not a neighbour)
+  int *err;                             // raised by a timed-out wait
+  int nranks;
+  int nghost;
+};
+
 struct HaloPlan {
   std::vector<int> send_count, send_off, recv_count, recv_off;   // per peer rank
   int32_t nsend = 0, nghost = 0;
@@ -128,14 +139,17 @@ struct HaloPlan {
   DevBuf<long long> d_peer_stride;       // per peer: its nghost (slot stride)
   DevBuf<int> d_send_off, d_send_cnt, d_recv_cnt;
   DevBuf<unsigned int> d_counter;
-  unsigned long long seq = 0;
-  const double *current_ghost = nullptr; // what the SpMV kernels read after the last exchange
+  DevBuf<unsigned long long> d_seq;      // device-resident sequence number: the exchange is CUDA-graph replayable
+  DevBuf<HaloWaitDev> d_wait;
+  const double *current_ghost = nullptr; // NCCL path: what the SpMV kernels read after the last exchange
   ~HaloPlan();
 };
-// posts the exchange of the ghost entries of x on `stream`; halo_wait makes them visible
-// (no-op for the NCCL path, flag wait for the peer-memory path)
+// posts the exchange of the ghost entries of x on `stream`.  NCCL path: complete in stream order.
+// Peer-memory path: the consumer kernel waits for the flags (HaloWaitDev, kernels.cu); halo_wait is
+// the stand-alone wait for host-side consumers (set-up)
 void halo_exchange(Ctx &c, HaloPlan &h, const double *x_own, cudaStream_t stream, ncclComm_t comm);
 void halo_wait(Ctx &c, HaloPlan &h, cudaStream_t stream);
+const double *halo_ghost_after_wait(Ctx &c, HaloPlan &h);      // host-side: pointer to the current ghost slot
 void halo_enable_p2p(Ctx &c, HaloPlan &h);
 
 // Device-resident CSR operator; columns index [x_own | x_ghost].
@@ -148,6 +162,7 @@ struct DevCsr {
   int32_t nghost = 0;        // columns [ncols_own, ncols_own+nghost) address the ghost buffer
   int64_t nnz = 0;
   int lanes = 8;             // lanes per row of the vector kernel, from the row-length histogram
+  int sell_warps = 1;        // warps per SELL slice (multi-warp kernel for operators with few rows)
   std::shared_ptr<HaloPlan> halo;   // null on single-rank contexts
   std::string tag;           // name used by the per-kernel timers ("A00", "A00/L1", "A00/P0", ...)
   DevBuf<int32_t> rowptr, col;
@@ -169,13 +184,28 @@ struct DevCsr {
 };
 
 // epilogues of the SpMV-class kernels ---------------------------------------
+// Optional second output of the store / axpby epilogues: y2 = s2 * d2 .* y, the first step of the
+// Chebyshev-Jacobi smoother that consumes y as its right-hand side (amg.cu) -- the restriction and
+// the residual of a V-cycle level hand the smoother its first iterate instead of leaving it a kernel
+// of its own.
 struct EpiStore {            // y = A x
   double *y;
+  double *y2 = nullptr;
+  const double *d2 = nullptr;
+  double s2 = 0.0;
 };
 struct EpiAxpby {            // y = a * (A x) + b * z          (z may alias y)
   double *y;
   const double *z;
   double a, b;
+  double *y2 = nullptr;
+  const double *d2 = nullptr;
+  double s2 = 0.0;
+};
+struct Jacobi1 {             // second output request: y2 = s2 * d2 .* y
+  double *y2 = nullptr;
+  const double *d2 = nullptr;
+  double s2 = 0.0;
 };
 struct EpiCheb {             // out = add + c0 p0 + c1 p1 + c2 dinv (b - A p1)   (p0, add optional)
   double *out;
@@ -191,8 +221,9 @@ struct EpiCheb {             // out = add + c0 p0 + c1 p1 + c2 dinv (b - A p1)  
 void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &tag, int64_t n_own_split = -1, int bs = 1,
                         int64_t n_own_cols = -1);
 void csr_set_values(Ctx &c, DevCsr &A, const HostCsr &pattern, const double *val, bool want_dinv);
-void spmv_store(Ctx &c, const DevCsr &A, const double *x, double *y);
-void spmv_axpby(Ctx &c, const DevCsr &A, const double *x, double a, double b, const double *z, double *y);
+void spmv_store(Ctx &c, const DevCsr &A, const double *x, double *y, const Jacobi1 &j = Jacobi1());
+void spmv_axpby(Ctx &c, const DevCsr &A, const double *x, double a, double b, const double *z, double *y,
+                const Jacobi1 &j = Jacobi1());
 void spmv_cheb(Ctx &c, const DevCsr &A, const EpiCheb &e);
 
 // BLAS-1 class kernels ------------------------------------------------------
@@ -211,6 +242,8 @@ void vec_scatter(Ctx &c, int64_t n, const int64_t *idx, const double *src, doubl
 // Vptrs_dev: device array of pointers to the basis vectors (allocated lazily).
 // h[i] = v_i . w for i < nvec
 void multi_dot_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int nvec, const double *w, double *h_dev);
+// same plus h[nvec] = w . w (the one-reduction Gram-Schmidt of gmres.cu)
+void multi_dot_ww_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int nvec, const double *w, double *h_dev);
 // w -= sum_i h[i] v_i ; nrm2_dev[0] = ||w||^2 (after the update)
 void multi_axpy_norm_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int nvec, const double *h_dev, double *w,
                           double *nrm2_dev);
@@ -291,7 +324,8 @@ struct DevHierarchy {
   bool built = false;
   // device-side Galerkin refresh (amg_refresh.cu): plan matrices W_l with A_{l+1}.val = W_l * A_l.val,
   // diagonal positions of the coarse levels
-  std::vector<DevCsr> refresh_W;
+  std::vector<std::vector<DevCsr>> refresh_W;       // per level: row chunks of the plan matrix
+  std::vector<std::vector<int64_t>> refresh_row0;   // first coarse value position of every chunk
   std::vector<DevBuf<int32_t>> refresh_diag;
   bool refresh_built = false;
   bool host_vals_stale = false;       // device-side refreshes since the host mirror was last synchronised
@@ -306,8 +340,11 @@ void amg_vcycle(Ctx &c, DevHierarchy &H, const double *b, double *x);
 
 // Chebyshev-Jacobi, zero initial guess, `steps` Jacobi applications:
 //   out = add + out_scale * cheb(A, b)
+// p1_ready: w0 already holds the first iterate s D^-1 b (written by the kernel that produced b, see
+// Jacobi1 / cheb_first_step_scale)
 void cheb_jacobi(Ctx &c, const DevCsr &A, const double *b, double emin, double emax, int steps,
-                 double out_scale, const double *add, double *out, double *w0, double *w1);
+                 double out_scale, const double *add, double *out, double *w0, double *w1, bool p1_ready = false);
+inline double cheb_first_step_scale(double emin, double emax) { return 2.0 / (emax + emin); }
 
 // ---------------------------------------------------------------------------
 // context
@@ -373,6 +410,9 @@ struct Ctx {
   int sell_gather = 95;         // SpMV kernel variant bits (kernels.cu): 1 wide gathers, 2 six CTAs/SM, 4 L2 prefetch, 8 wide epilogue (SELL);
                                 // 16 L2 prefetch in the CSR sub-warp kernel (experimental)
   int sell_sigma = 1024;        // SELL sorting window (rows)
+  int64_t refresh_chunk_terms = (int64_t)1 << 30;   // Galerkin refresh plan: terms per device chunk (option fnp_refresh_chunk_terms)
+  int64_t sell_warps_rows = 600000;                  // multi-warp SELL kernel below this many threads (option fnp_sell_warps_rows)
+  int sell_warps = 0;           // warps per SELL slice: 0 auto (from rows x mean row), 1 / 2 / 4 / 8 forced
   double sell_max_mean_row = 64.0;   // auto: operators with a longer mean row keep CSR + sub-warp per row
   int timers_on = 0;            // 0 off, 1 stage timers, 2 also one timer per SpMV launch
 
@@ -424,8 +464,8 @@ struct Ctx {
 
   // CUDA graph of one block-triangular PC apply on fixed staging buffers (single-rank
   // contexts): ~500 short launches per apply collapse into one graph launch
-  int p2p = 0;                  // 1: peer-memory halo exchange (cudaIpc stores + flags).  Correct, but measured slower
-                                // than NCCL send/recv inside a CUDA graph (4.6 vs 3.7 ms per apply at N=2), so opt-in
+  int p2p = 1;                  // 1: peer-memory halo exchange (cudaIpc stores + flags, wait fused into the consumer
+                                // kernel, device-resident sequence numbers); 0: NCCL send/recv
   DevBuf<int> p2p_err;          // set by a timed-out flag wait
   int overlap = 0;              // 1: split SELL operators into interior/boundary rows and overlap the halo exchange
                                 // on a second stream/communicator (measured SLOWER with NCCL send/recv: 5.8 vs 4.9 ms per apply)
@@ -438,6 +478,11 @@ struct Ctx {
   // Krylov basis
   std::vector<DevBuf<double>> V, Z;
   DevBuf<double> kr_w, kr_x, kr_b;
+  DevBuf<double> kr_H, kr_small;        // device-resident Hessenberg matrix, rotations, residual estimates (gmres.cu)
+  std::vector<cudaEvent_t> ev_iter;     // one event per in-flight iteration (two)
+  bool gmres_two_reductions = false;    // multi-rank: explicit norm with its own all-reduce (set after a cancellation)
+  int gmres_sync = 0;                   // option fnp_gmres_sync: look at every iteration's result before the next is enqueued
+  int converged_reason = 0;             // KSPConvergedReason of the last solve (2 rtol, 3 atol, -3 iterations)
   DevBuf<double> sol_x, sol_b, sol_m;   // staging of the user's b / x (split and monolithic layouts)
   std::vector<double> res_hist;
 

@@ -32,9 +32,14 @@ static inline int blocks_for(const Ctx &c, int64_t n, int threads, int per_sm) {
 // ---------------------------------------------------------------------------
 // SpMV
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue(const EpiStore &e, int r, double s) { e.y[r] = s; }
+__device__ __forceinline__ void epilogue(const EpiStore &e, int r, double s) {
+  e.y[r] = s;
+  if (e.y2) e.y2[r] = e.s2 * e.d2[r] * s;
+}
 __device__ __forceinline__ void epilogue(const EpiAxpby &e, int r, double s) {
-  e.y[r] = e.a * s + e.b * e.z[r];
+  const double v = e.a * s + e.b * e.z[r];
+  e.y[r] = v;
+  if (e.y2) e.y2[r] = e.s2 * e.d2[r] * v;
 }
 __device__ __forceinline__ void epilogue(const EpiCheb &e, int r, double s) {
   double v = e.c1 * e.p1[r] + e.c2 * e.dinv[r] * (e.b[r] - s);
@@ -54,6 +59,31 @@ __device__ __forceinline__ void epilogue(const EpiCheb &e, int r, double s) {
 template <int BS>
 __device__ __forceinline__ const double *gather_ptr(const double *__restrict__ x, const double *__restrict__ xg, int nown, int c) {
   return c < nown ? x + (int64_t)BS * c : xg + (int64_t)BS * (c - nown);
+}
+
+// Peer-memory halo exchange (dist.cu): the ghost entries are stored into this GPU's arena by the
+// neighbouring GPUs, which then publish the exchange's sequence number in this GPU's flag words.  A
+// kernel that consumes ghosts waits here -- thread 0 of every block spins (bounded) until every
+// neighbour's flag has reached the sequence number of the exchange posted just before the launch
+// -- and takes the ghost slot of that exchange.  No thread touches the arena before the barrier,
+// so no cache of this SM can hold a stale line of it.
+__device__ __forceinline__ const double *halo_wait_dev(const HaloWaitDev *__restrict__ hw) {
+  const unsigned long long seq = *hw->seq;
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int q = 0; q < hw->nranks; ++q) {
+      if (hw->recv_cnt[q] == 0) continue;
+      while (*((volatile const unsigned long long *)(hw->flags + q)) < seq) {
+        if (clock64() - t0 > 8000000000ll) {       // ~4 s: a neighbour died or fell out of step
+          *hw->err = 1;
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  return hw->arena + (size_t)(seq & 1ull) * (size_t)hw->nghost;
 }
 
 // The three components of node c with two 16-byte loads instead of three 8-byte ones: the
@@ -79,7 +109,8 @@ template <int LANES, int BS, class Epi, bool PF>
 __global__ void __launch_bounds__(256)
 spmv_kernel(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             const double *__restrict__ val, const double *__restrict__ x, const double *__restrict__ xg, int nown,
-            Epi epi) {
+            const HaloWaitDev *__restrict__ hw, Epi epi) {
+  if (hw) xg = halo_wait_dev(hw);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = tid / LANES;
   const int lane = tid % LANES;
@@ -220,15 +251,30 @@ __device__ __forceinline__ void load3(const double *p, bool wide, double (&o)[3]
     o[2] = p[2];
   }
 }
-__device__ __forceinline__ void epilogue3(const EpiStore &e, int r, const double (&s)[3], bool) {
+__device__ __forceinline__ void epilogue3(const EpiStore &e, int r, const double (&s)[3], bool wide) {
 #pragma unroll
   for (int b = 0; b < 3; ++b) e.y[3 * r + b] = s[b];
+  if (e.y2) {
+    double d[3];
+    load3(e.d2 + 3 * r, wide, d);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) e.y2[3 * r + b] = e.s2 * d[b] * s[b];
+  }
 }
 __device__ __forceinline__ void epilogue3(const EpiAxpby &e, int r, const double (&s)[3], bool wide) {
-  double z[3];
+  double z[3], v[3];
   load3(e.z + 3 * r, wide, z);
 #pragma unroll
-  for (int b = 0; b < 3; ++b) e.y[3 * r + b] = e.a * s[b] + e.b * z[b];
+  for (int b = 0; b < 3; ++b) {
+    v[b] = e.a * s[b] + e.b * z[b];
+    e.y[3 * r + b] = v[b];
+  }
+  if (e.y2) {
+    double d[3];
+    load3(e.d2 + 3 * r, wide, d);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) e.y2[3 * r + b] = e.s2 * d[b] * v[b];
+  }
 }
 __device__ __forceinline__ void epilogue3(const EpiCheb &e, int r, const double (&s)[3], bool wide) {
   double p1[3], di[3], bb[3], v[3];
@@ -270,7 +316,8 @@ template <int BS, class Epi, int VAR>
 __global__ void __launch_bounds__(256, (VAR & 2) ? 6 : 0)
 spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t *__restrict__ col,
                  const double *__restrict__ val, const int32_t *__restrict__ perm, const double *__restrict__ x,
-                 const double *__restrict__ xg, int nown, Epi epi) {
+                 const double *__restrict__ xg, int nown, const HaloWaitDev *__restrict__ hw, Epi epi) {
+  if (hw) xg = halo_wait_dev(hw);
   const int slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (slice >= nslices) return;
@@ -317,6 +364,100 @@ spmv_sell_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t 
       }
     }
   }
+}
+
+// Multi-warp SELL kernel for operators with too few rows to fill the GPU with one thread per row
+// (AMG levels 1.., the pressure operators of small meshes): T warps share a slice, warp t takes the
+// entries k = t, t + T, ... of its 32 rows -- every load stays a coalesced 32-entry column of the
+// slice, the layout is the one of the single-warp kernel -- and the T partial sums meet in shared
+// memory (fixed order: deterministic).  Round-1 profile of the case it is for: level 1 of the
+// velocity hierarchy, 207 k rows x 51 entries, one thread per row = 44 warps per SM each walking a
+// 51-long dependent col -> x[col] chain, 0.21 of the HBM peak.
+template <int BS, class Epi, int T, bool L2RES>
+__global__ void __launch_bounds__(256)
+spmv_sell_mw_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32_t *__restrict__ col,
+                    const double *__restrict__ val, const int32_t *__restrict__ perm, const double *__restrict__ x,
+                    const double *__restrict__ xg, int nown, const HaloWaitDev *__restrict__ hw, Epi epi) {
+  if (hw) xg = halo_wait_dev(hw);
+  constexpr int SPB = 8 / T;                       // slices per block of 8 warps
+  __shared__ double part[8][BS][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = warp % T;
+  const int slice = blockIdx.x * SPB + warp / T;
+  const bool valid = slice < nslices;
+  double s0[BS], s1[BS];
+#pragma unroll
+  for (int b = 0; b < BS; ++b) s0[b] = s1[b] = 0.0;
+  bool narrow = false;
+  if (valid) {
+    const int raw = __ldg(sl_ptr + slice);
+    const int base = raw & ~(SELL_C - 1);
+    narrow = (raw & SELL_NARROW) != 0;
+    const int len = ((__ldg(sl_ptr + slice + 1) & ~(SELL_C - 1)) - base) >> 5;
+    const int32_t *cp = col + base + lane;
+    const double *vp = val + base + lane;
+    auto ldi = [](const int32_t *p) { return L2RES ? __ldg(p) : __ldcs(p); };
+    auto ldd = [](const double *p) { return L2RES ? __ldg(p) : __ldcs(p); };
+    const bool wide = BS == 3 && !narrow;
+    int k = t;
+    for (; k + T < len; k += 2 * T) {
+      const int c0 = ldi(cp + k * SELL_C), c1 = ldi(cp + (k + T) * SELL_C);
+      const double v0 = ldd(vp + k * SELL_C), v1 = ldd(vp + (k + T) * SELL_C);
+      const double *p0 = gather_ptr<BS>(x, xg, nown, c0), *p1 = gather_ptr<BS>(x, xg, nown, c1);
+      double x0[BS], x1[BS];
+      if constexpr (BS == 3) {
+        if (wide) {
+          gather3_wide(p0, x0[0], x0[1], x0[2]);
+          gather3_wide(p1, x1[0], x1[1], x1[2]);
+        } else {
+#pragma unroll
+          for (int b = 0; b < BS; ++b) { x0[b] = __ldg(p0 + b); x1[b] = __ldg(p1 + b); }
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < BS; ++b) { x0[b] = __ldg(p0 + b); x1[b] = __ldg(p1 + b); }
+      }
+#pragma unroll
+      for (int b = 0; b < BS; ++b) {
+        s0[b] += v0 * x0[b];
+        s1[b] += v1 * x1[b];
+      }
+    }
+    if (k < len) {
+      const double v0 = ldd(vp + k * SELL_C);
+      const double *p0 = gather_ptr<BS>(x, xg, nown, ldi(cp + k * SELL_C));
+#pragma unroll
+      for (int b = 0; b < BS; ++b) s0[b] += v0 * __ldg(p0 + b);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < BS; ++b) part[warp][b][lane] = s0[b] + s1[b];
+  __syncthreads();
+  if (!valid || t != 0) return;
+  const int row = __ldg(perm + slice * SELL_C + lane);
+  if (row < 0) return;
+  double s[BS];
+#pragma unroll
+  for (int b = 0; b < BS; ++b) {
+    double acc = part[warp][b][lane];
+#pragma unroll
+    for (int q = 1; q < T; ++q) acc += part[warp + q][b][lane];
+    s[b] = acc;
+  }
+  if constexpr (BS == 3) {
+    epilogue3(epi, row, s, !narrow);
+  } else {
+#pragma unroll
+    for (int b = 0; b < BS; ++b) epilogue(epi, BS * row + b, s[b]);
+  }
+}
+
+// warps per slice of the multi-warp kernel: enough threads to fill the GPU (~600 k), at least
+// ~6 entries per lane
+static int pick_sell_warps(int64_t nrows, double mean_row, int64_t target_threads) {
+  int t = 1;
+  while (t < 8 && nrows * t < target_threads && mean_row / (2 * t) >= 6.0) t *= 2;
+  return t;
 }
 
 static int pick_lanes(double mean_row) {
@@ -456,6 +597,7 @@ void csr_upload_pattern(Ctx &c, DevCsr &A, const HostCsr &h, const std::string &
   for (int64_t i = 0; i < h.nrows; ++i) maxrow = std::max(maxrow, (double)(h.rowptr[i + 1] - h.rowptr[i]));
   A.max_row = maxrow;
   A.lanes = pick_lanes(A.mean_row);
+  A.sell_warps = c.sell_warps > 0 ? c.sell_warps : pick_sell_warps(h.nrows, A.mean_row, c.sell_warps_rows);
   A.has_dinv = false;
   A.sell = false;
   A.rowptr.upload(h.rowptr.data(), h.rowptr.size(), c.stream);
@@ -515,13 +657,34 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
     xg = A.halo->current_ghost;
     nown = A.ncols_own;
   }
+  // peer-memory exchange: the kernel that reads ghosts waits for the neighbours' flags itself and
+  // derives the ghost slot from the device-resident sequence number (graph replayable)
+  const HaloWaitDev *hw_ghost = (A.halo && A.halo->p2p && A.halo->nghost > 0) ? A.halo->d_wait.p : nullptr;
   StageTimer kt(c, "spmv " + A.tag, 2, A.spmv_bytes());
   if (A.sell) {
-    auto launch = [&](int nsl, const int32_t *ptr, const int32_t *perm, int64_t off) {
+    auto launch = [&](int nsl, const int32_t *ptr, const int32_t *perm, int64_t off, const HaloWaitDev *hw) {
       if (nsl <= 0) return;
+      if (A.sell_warps > 1) {
+        const int T = A.sell_warps;
+        const int gridw = (nsl + 8 / T - 1) / (8 / T);
+        const bool l2res = (c.sell_gather & 64) && A.spmv_bytes() <= 64e6;
+#define FNP_SELL_MW(TT)                                                                                                          \
+  do {                                                                                                                       \
+    if (l2res)                                                                                                               \
+      spmv_sell_mw_kernel<BS, Epi, TT, true><<<gridw, 256, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, hw, epi);  \
+    else                                                                                                                     \
+      spmv_sell_mw_kernel<BS, Epi, TT, false><<<gridw, 256, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, hw, epi); \
+  } while (0)
+        if (T == 2) FNP_SELL_MW(2);
+        else if (T == 4) FNP_SELL_MW(4);
+        else FNP_SELL_MW(8);
+#undef FNP_SELL_MW
+        FNP_LAUNCH_CHECK(c);
+        return;
+      }
       const int grid = (int)(((int64_t)nsl * 32 + threads - 1) / threads);
 #define FNP_SELL(V) \
-  spmv_sell_kernel<BS, Epi, V><<<grid, threads, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, epi)
+  spmv_sell_kernel<BS, Epi, V><<<grid, threads, 0, c.stream>>>(nsl, ptr, A.sl_col.p + off, A.sl_val.p + off, perm, x, xg, nown, hw, epi)
       if (BS == 3) {
         switch (c.sell_gather & 15) {
           case 0: FNP_SELL(0); break;
@@ -539,26 +702,24 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
       FNP_LAUNCH_CHECK(c);
     };
     if (A.halo && A.nslices_b > 0) {
-      // split operator: the interior rows run while the ghost entries are in flight,
-      // the flag wait sits between the two passes (same stream, no extra events)
-      launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0);
-      halo_wait(c, *A.halo, c.stream);
-      launch(A.nslices_b, A.sl_ptr_b.p, A.sl_perm_b.p, A.sell_entries_a);
+      // split operator: the interior rows (no ghost column) run while the ghost entries are in
+      // flight; the boundary rows wait for the flags inside their kernel
+      launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0, nullptr);
+      launch(A.nslices_b, A.sl_ptr_b.p, A.sl_perm_b.p, A.sell_entries_a, hw_ghost);
     } else {
-      if (A.halo) halo_wait(c, *A.halo, c.stream);
-      launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0);
-      launch(A.nslices_b, A.sl_ptr_b.p, A.sl_perm_b.p, A.sell_entries_a);
+      launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0, hw_ghost);
+      launch(A.nslices_b, A.sl_ptr_b.p, A.sl_perm_b.p, A.sell_entries_a, hw_ghost);
     }
     return;
   }
-  if (A.halo) halo_wait(c, *A.halo, c.stream);
+  const HaloWaitDev *hwc = hw_ghost;
   auto grid = [&](int lanes) { return (int)(((int64_t)A.nrows * lanes + threads - 1) / threads); };
 #define FNP_VEC(L)                                                                                                        \
   do {                                                                                                                \
     if (c.sell_gather & 16)                                                                                           \
-      spmv_kernel<L, BS, Epi, true><<<grid(L), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi);  \
+      spmv_kernel<L, BS, Epi, true><<<grid(L), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, hwc, epi);  \
     else                                                                                                              \
-      spmv_kernel<L, BS, Epi, false><<<grid(L), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, epi); \
+      spmv_kernel<L, BS, Epi, false><<<grid(L), threads, 0, c.stream>>>(A.nrows, A.rowptr.p, A.col.p, A.val.p, x, xg, nown, hwc, epi); \
   } while (0)
   switch (A.lanes) {
     case 2: FNP_VEC(2); break;
@@ -582,9 +743,11 @@ static void spmv_launch(Ctx &c, const DevCsr &A, const double *x, const Epi &epi
   }
 }
 
-void spmv_store(Ctx &c, const DevCsr &A, const double *x, double *y) { spmv_launch(c, A, x, EpiStore{y}); }
-void spmv_axpby(Ctx &c, const DevCsr &A, const double *x, double a, double b, const double *z, double *y) {
-  spmv_launch(c, A, x, EpiAxpby{y, z, a, b});
+void spmv_store(Ctx &c, const DevCsr &A, const double *x, double *y, const Jacobi1 &j) {
+  spmv_launch(c, A, x, EpiStore{y, j.y2, j.d2, j.s2});
+}
+void spmv_axpby(Ctx &c, const DevCsr &A, const double *x, double a, double b, const double *z, double *y, const Jacobi1 &j) {
+  spmv_launch(c, A, x, EpiAxpby{y, z, a, b, j.y2, j.d2, j.s2});
 }
 void spmv_cheb(Ctx &c, const DevCsr &A, const EpiCheb &e) { spmv_launch(c, A, e.p1, e); }
 
@@ -666,11 +829,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 // stage 1: partial[(i) * gridDim.x + blockIdx.x] = sum over this block's elements of V_i[e] * w[e]
 __global__ void __launch_bounds__(RED_THREADS)
 multidot_kernel(int64_t n, const double *const *__restrict__ V, int nvec, const double *__restrict__ w,
-                double *__restrict__ partial) {
+                double *__restrict__ partial, int nbasis) {
+  // slots [0, nbasis) are basis vectors, slot nbasis (when nvec = nbasis + 1) is w itself: w . w
   const int i0 = blockIdx.y * DOT_BATCH;
   const double *v[DOT_BATCH];
 #pragma unroll
-  for (int b = 0; b < DOT_BATCH; ++b) v[b] = V[min(i0 + b, nvec - 1)];
+  for (int b = 0; b < DOT_BATCH; ++b) v[b] = (i0 + b < nbasis) ? V[i0 + b] : (nvec > nbasis ? w : V[nbasis - 1]);
   double acc[DOT_BATCH];
 #pragma unroll
   for (int b = 0; b < DOT_BATCH; ++b) acc[b] = 0.0;
@@ -720,7 +884,19 @@ void multi_dot_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int nvec,
   StageTimer kt(c, "multidot", 2, 8.0 * n * (nvec + (nvec + DOT_BATCH - 1) / DOT_BATCH));
   c.red_partial.ensure((size_t)nblk * (nvec + DOT_BATCH));
   dim3 grid(nblk, (nvec + DOT_BATCH - 1) / DOT_BATCH);
-  multidot_kernel<<<grid, RED_THREADS, 0, c.stream>>>(n, Vptrs_dev, nvec, w, c.red_partial.p);
+  multidot_kernel<<<grid, RED_THREADS, 0, c.stream>>>(n, Vptrs_dev, nvec, w, c.red_partial.p, nvec);
+  FNP_LAUNCH_CHECK(c);
+  reduce_partials_kernel<<<nvec, 128, 0, c.stream>>>(c.red_partial.p, nblk, h_dev);
+  FNP_LAUNCH_CHECK(c);
+}
+
+void multi_dot_ww_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int nbasis, const double *w, double *h_dev) {
+  const int nvec = nbasis + 1;
+  const int nblk = red_blocks(c, n);
+  StageTimer kt(c, "multidot", 2, 8.0 * n * (nvec + (nvec + DOT_BATCH - 1) / DOT_BATCH));
+  FNP_REQUIRE(c.red_partial.n >= (size_t)nblk * (nvec + DOT_BATCH), FNP_ERR_STATE, "reduction work space too small");
+  dim3 grid(nblk, (nvec + DOT_BATCH - 1) / DOT_BATCH);
+  multidot_kernel<<<grid, RED_THREADS, 0, c.stream>>>(n, Vptrs_dev, nvec, w, c.red_partial.p, nbasis);
   FNP_LAUNCH_CHECK(c);
   reduce_partials_kernel<<<nvec, 128, 0, c.stream>>>(c.red_partial.p, nblk, h_dev);
   FNP_LAUNCH_CHECK(c);

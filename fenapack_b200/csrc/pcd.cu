@@ -185,8 +185,9 @@ void Ctx::drop_graph() {
 
 void pc_apply_vec(Ctx &c, const double *x, double *y) {
   const int64_t n = c.n_u + c.n_p;
-  // multi-rank: the apply contains NCCL send/recv (capturable since NCCL 2.9); opt-in with fnp_cuda_graph 2
-  const bool graphable = c.use_graph && (c.nranks == 1 || (c.use_graph >= 2 && !c.p2p)) && c.timers_on == 0 &&
+  // multi-rank: the apply contains peer-memory exchanges (device-resident sequence numbers) or NCCL
+  // send/recv and all-gathers (capturable since NCCL 2.9); fnp_cuda_graph 1 restricts graphs to one rank
+  const bool graphable = c.use_graph && (c.nranks == 1 || c.use_graph >= 2) && c.timers_on == 0 &&
                          c.stream != nullptr;   // the legacy default stream cannot be captured
   if (!graphable) {
     pc_apply(c, x, x + c.n_u, y, y + c.n_u);

@@ -17,7 +17,7 @@ from fenapack_b200 import capi  # noqa: E402
 
 n1 = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-prob = bi.OseenBoxProblem(n1, n1, n1, kind="cavity", variant="BRM2", device="cuda:0")
+prob = bi.generate(n1, n1, n1, kind="cavity", variant="BRM2", device="cuda:0")
 torch.cuda.empty_cache()
 ctx = capi.Context(0)
 opts = dict(bench.OPTIONS)
