@@ -54,7 +54,24 @@ OPTIONS = {
     "fieldsplit_p_PCD_Mp_ksp_max_it": 5,
     "fieldsplit_p_PCD_Mp_ksp_chebyshev_eigenvalues": "0.5, 2.5",
     "fieldsplit_p_PCD_Mp_pc_type": "jacobi",
+    # SA-AMG settings of the bench (library defaults: eig_ratio 10, coarse_size 400): Chebyshev smoother
+    # on [rho/4, rho], velocity hierarchy stopped at <= 2000 rows (dense inverse).  Round-2 sweep on the
+    # 64^3 / 128^3 cavities: 21 -> 17 and 19 -> 17 outer iterations (profiles/r02_tuning_sweep.md)
+    "fieldsplit_u_pc_amg_eig_ratio": 4,
+    "fieldsplit_p_PCD_Ap_pc_amg_eig_ratio": 4,
+    "fieldsplit_u_pc_amg_coarse_size": 2000,
 }
+
+
+def oracle_amg_kwargs(prefix, opts=None):
+    """The SA-AMG settings of OPTIONS as keyword arguments of the oracle's set-up / V-cycle."""
+    opts = OPTIONS if opts is None else opts
+    kw = {}
+    if prefix + "pc_amg_eig_ratio" in opts:
+        kw["eig_ratio"] = float(opts[prefix + "pc_amg_eig_ratio"])
+    if prefix + "pc_amg_coarse_size" in opts:
+        kw["coarse_size"] = int(opts[prefix + "pc_amg_coarse_size"])
+    return kw
 
 
 def parse_args():
@@ -201,13 +218,16 @@ def cpu_port_sample(prob, hier_u, hier_p, variant, its, rtol=1e-6):
     return nap / dt, dt, n_it, cref.num_threads(), hist
 
 
-def oracle_hierarchies_from_library(ctx):
+def oracle_hierarchies_from_library(ctx, opts=None):
     """The hierarchies the GPU library built, as oracle objects (same inner operators
     on both sides)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from fenapack_b200 import capi
     from util import oracle_hierarchy_from_device
-    return oracle_hierarchy_from_device(ctx, capi.MAT_A00), oracle_hierarchy_from_device(ctx, capi.MAT_AP)
+    eu = oracle_amg_kwargs("fieldsplit_u_", opts).get("eig_ratio", 10.0)
+    ep = oracle_amg_kwargs("fieldsplit_p_PCD_Ap_", opts).get("eig_ratio", 10.0)
+    return (oracle_hierarchy_from_device(ctx, capi.MAT_A00, eig_ratio=eu),
+            oracle_hierarchy_from_device(ctx, capi.MAT_AP, eig_ratio=ep))
 
 
 # ---------------------------------------------------------------------------
@@ -513,7 +533,7 @@ def b200_arm(args):
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample ----
     if world == 1 and not args.no_cpu_baseline and not args.profile_only:
         try:
-            Hu, Hp = oracle_hierarchies_from_library(ctx)
+            Hu, Hp = oracle_hierarchies_from_library(ctx, opts)
             v, dt, n_it, thr, chist = cpu_port_sample(prob, Hu, Hp, variant, args.cpu_sample_its)
             k = min(len(chist), len(hist)) - 1
             result["cpu_baseline"] = {
@@ -555,10 +575,8 @@ def reference_arm(args):
     t0 = time.perf_counter()
     # same hierarchy arrangement as the library (velocity block = S (x) I_3: S is coarsened);
     # the CPU arm itself works on the general CSR format, as PETSc's AIJ would
-    kw_u = {"coarse_size": int(OPTIONS["fieldsplit_u_pc_amg_coarse_size"])} if "fieldsplit_u_pc_amg_coarse_size" in OPTIONS else {}
-    kw_p = {"coarse_size": int(OPTIONS["fieldsplit_p_PCD_Ap_pc_amg_coarse_size"])} if "fieldsplit_p_PCD_Ap_pc_amg_coarse_size" in OPTIONS else {}
-    Hu = oamg.build_hierarchy_kron(prob.scipy("A00"), bs=3, **kw_u)
-    Hp = oamg.build_hierarchy(prob.scipy("Ap"), **kw_p)
+    Hu = oamg.build_hierarchy_kron(prob.scipy("A00"), bs=3, S=prob.scipy("S00"), **oracle_amg_kwargs("fieldsplit_u_"))
+    Hp = oamg.build_hierarchy(prob.scipy("Ap"), **oracle_amg_kwargs("fieldsplit_p_PCD_Ap_"))
     t_setup = time.perf_counter() - t0
     mats = {k: prob.scipy(k) for k in ("A00", "A01", "A10", "Ap", "Mp", "Kp")}
     pc = cref.CPCD(mats, variant, prob.bc_idx, prob.bc_val, Hu, Hp, prob.cheb_bounds)

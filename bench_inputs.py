@@ -305,6 +305,7 @@ class OseenBoxProblem:
             ci3[pos] = 3 * ci + comp
             va3[pos] = va
         self.A00 = (rp3.astype(np.int32), ci3, va3)
+        self.S00 = (rp, ci, va)          # the scalar operator: A00 = S00 (x) I_3, local node rows, global node columns
         bu_h = bu.cpu().numpy()
         gv = gval_own[isbc_own].cpu().numpy()
         bidx = (3 * (bcn - self.node_begin).cpu().numpy()[:, None] + np.arange(3)[None]).ravel()
@@ -330,7 +331,7 @@ class OseenBoxProblem:
     def scipy(self, name):
         import scipy.sparse as sp
         rp, ci, va = getattr(self, name)
-        ncols = {"A00": self.n_u_global, "A10": self.n_u_global}.get(name, self.n_p_global)
+        ncols = {"A00": self.n_u_global, "A10": self.n_u_global, "S00": self.n_u_global // 3}.get(name, self.n_p_global)
         return sp.csr_matrix((va, ci, rp), shape=(rp.size - 1, ncols))
 
 
@@ -340,7 +341,7 @@ class MergedProblem:
     are global already.  Bounds the generator's device memory at large n (one slab of the 128^3
     cavity needs as much as the whole 64^3 one)."""
 
-    OPS = ("A00", "A01", "A10", "Ap", "Mp", "Kp")
+    OPS = ("A00", "A01", "A10", "Ap", "Mp", "Kp", "S00")
 
     def __init__(self, parts):
         p0, pl = parts[0], parts[-1]

@@ -1,13 +1,15 @@
 """Form bookkeeping of the PCD preconditioner -- drop-in for fenapack/assembling.py.
 
-Assembly stays on the host (BASELINE.json north_star).  With DOLFIN the
-``a, L, mp, ap, kp ...`` arguments are UFL forms and the work is delegated to
-``dolfin.SystemAssembler`` / ``dolfin.assemble`` exactly as the reference does
-(assembling.py:85-180).  Without DOLFIN (this image) every "form" is a *host
-assembler callable* ``form() -> scipy.sparse matrix`` (or vector) on the full
-mixed space in monolithic numbering, and a boundary condition is any object with
-``dofs()`` (monolithic indices) and ``values()``.  Either way the contract seen
-by PCDInterface is the same: tensors on the mixed space W.
+Assembly stays on the host (BASELINE.json north_star).  In the reference the
+``a, L, mp, ap, kp ...`` arguments are UFL forms handed to ``dolfin.SystemAssembler`` /
+``dolfin.assemble`` (assembling.py:85-180).  DOLFIN is not available in this image and that
+branch is NOT implemented here (UFL forms raise ``NotImplementedError``): every "form" is a
+*host assembler callable* ``form() -> scipy.sparse matrix`` (or vector) on the mixed space in
+monolithic numbering -- this rank's rows when the function space reports an ownership range,
+the whole tensor otherwise -- and a boundary condition is any object with ``dofs()``
+(monolithic indices, all constrained dofs) and ``values()``.  A FEniCS user wraps
+``lambda: as_scipy(assemble(form))``; the contract seen by PCDInterface is the same:
+tensors on the mixed space W.
 
 BC semantics kept from the reference: the system / preconditioner matrix and the
 right-hand side get ``bcs`` the way ``SystemAssembler`` applies them (symmetric
@@ -66,28 +68,33 @@ def _bc_dofs_values(bcs):
     return dofs, vals
 
 
-def _dirichlet_rows(A, dofs):
+def _dirichlet_rows(A, dofs, row0=0):
     """``DirichletBC.apply(A)`` (MatZeroRows with unit diagonal): rows of ``dofs`` zeroed,
     diagonal set to one (added when the form's pattern lacks it; it lies outside every
     off-diagonal split block).  The zeroed entries leave the pattern; ``gp`` is a constant
-    form, assembled once, so no later refresh depends on them."""
+    form, assembled once, so no later refresh depends on them.  ``A`` holds the rows
+    ``row0 ..`` of the global matrix (row partition); ``dofs`` are global ids."""
     A = sp.csr_matrix(A, copy=True)
-    mask = np.zeros(A.shape[0], dtype=bool)
+    mask = np.zeros(A.shape[1], dtype=bool)
     mask[dofs] = True
-    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr)) + row0
     A.data[mask[rows]] = 0.0
-    A = (A + sp.diags(mask.astype(np.float64), shape=A.shape, format="csr")).tocsr()
+    loc = np.arange(A.shape[0])
+    own = mask[loc + row0]
+    D = sp.csr_matrix((own.astype(np.float64)[own], (loc[own], loc[own] + row0)), shape=A.shape)
+    A = (A + D).tocsr()
     A.sort_indices()
     return A
 
 
-def _symmetric_dirichlet(A, dofs):
+def _symmetric_dirichlet(A, dofs, row0=0):
     """Rows and columns of ``dofs`` zeroed, unit diagonal (what
-    ``SystemAssembler`` does to the matrix); the pattern is kept."""
+    ``SystemAssembler`` does to the matrix); the pattern is kept.  Row-partition aware as
+    ``_dirichlet_rows``."""
     A = sp.csr_matrix(A, copy=True)
-    mask = np.zeros(A.shape[0], dtype=bool)
+    mask = np.zeros(A.shape[1], dtype=bool)
     mask[dofs] = True
-    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr)) + row0
     kill = mask[rows] | mask[A.indices]
     A.data[kill] = 0.0
     A.data[kill & (rows == A.indices)] = 1.0
@@ -114,10 +121,20 @@ class PCDAssembler(object):
         for key, f in (("ap", ap), ("mp", mp), ("mu", mu), ("fp", fp), ("kp", kp), ("gp", gp)):
             if isinstance(f, PCDForm):
                 self._forms[key] = f
-        if HAVE_DOLFIN and function_space is None and hasattr(a, "arguments"):  # pragma: no cover
-            self._W = a.arguments()[0].function_space()
-            self._assembler = dolfin.SystemAssembler(a, L, self._bcs)
-            self._assembler_pc = dolfin.SystemAssembler(a_pc, L, self._bcs) if a_pc is not None else None
+        if function_space is None and hasattr(L, "arguments"):  # pragma: no cover - UFL forms need DOLFIN
+            # reference assembling.py:98: the test function's space
+            self._W = L.arguments()[0].function_space()
+        if not all(callable(f) or f is None or isinstance(f, PCDForm) or sp.issparse(f) or isinstance(f, np.ndarray)
+                   for f in (a, L, a_pc, mp, mu, ap, fp, kp, gp)):
+            raise NotImplementedError(
+                "PCDAssembler: UFL forms need DOLFIN's SystemAssembler / assemble (reference assembling.py:85-180), "
+                "which is not available here; pass host assembler callables returning scipy matrices instead")
+        # row partition: every callable returns this rank's rows [row0, row1) of the tensor on the mixed
+        # space (DOLFIN: GenericDofMap.ownership_range); one rank owns everything
+        self._rows = None
+        dm = getattr(self._W, "dofmap", None)
+        if callable(dm) and hasattr(dm(), "ownership_range"):
+            self._rows = tuple(int(v) for v in dm().ownership_range())
 
     # -- accessors -----------------------------------------------------------
     def function_space(self):
@@ -156,20 +173,35 @@ class PCDAssembler(object):
         ``g - x`` at the BC dofs in the Newton variant ``assemble(b, x)``)."""
         dofs, g = _bc_dofs_values(self._bcs)
         A = sp.csr_matrix(self._assemble(a_form, "a"))
+        row0 = self._row0()
         rhs = None
         if b is not None:
             rhs = np.array(self._assemble(self._L, "L"), dtype=np.float64)
             if dofs.size:
                 if x is not None:
-                    g = g - np.asarray(x.array if hasattr(x, "array") else x)[dofs]
+                    xa = np.asarray(x.array if hasattr(x, "array") else x)
+                    if xa.size != A.shape[1]:
+                        # row-partitioned iterate: the lifting needs the values at every constrained dof
+                        xa = np.concatenate(x.comm.allgather(xa))
+                    g = g - xa[dofs]
                 lift = np.zeros(A.shape[1])
                 lift[dofs] = g
                 rhs = rhs - A @ lift
-                rhs[dofs] = g
-        return (_symmetric_dirichlet(A, dofs) if dofs.size else A), rhs
+                own = (dofs >= row0) & (dofs < row0 + A.shape[0])
+                rhs[dofs[own] - row0] = g[own]
+        return (_symmetric_dirichlet(A, dofs, row0) if dofs.size else A), rhs
+
+    def _row0(self):
+        return self._rows[0] if self._rows is not None else 0
+
+    def _fill(self, mat, csr):
+        if self._rows is not None:
+            mat.set_csr(csr, row_range=self._rows)
+        else:
+            mat.set_csr(csr)
 
     def system_matrix(self, A):
-        A.set_csr(self._system(self._a)[0])
+        self._fill(A, self._system(self._a)[0])
 
     def rhs_vector(self, b, x=None):
         b.array[:] = self._system(self._a, b, x)[1]
@@ -177,30 +209,30 @@ class PCDAssembler(object):
     def pc_matrix(self, P):
         if self._a_pc is None:
             return None
-        P.set_csr(self._system(self._a_pc)[0])
+        self._fill(P, self._system(self._a_pc)[0])
         return P
 
     # -- PCD operators on the mixed space --------------------------------------
     def ap(self, Ap):
         A = self._assemble(self.get_dolfin_form("ap"), "ap")
         dofs, _ = _bc_dofs_values(self.pcd_bcs())
-        Ap.set_csr(_symmetric_dirichlet(A, dofs))
+        self._fill(Ap, _symmetric_dirichlet(A, dofs, self._row0()))
 
     def mp(self, Mp):
-        Mp.set_csr(self._assemble(self.get_dolfin_form("mp"), "mp"))
+        self._fill(Mp, self._assemble(self.get_dolfin_form("mp"), "mp"))
 
     def mu(self, Mu):
-        Mu.set_csr(self._assemble(self.get_dolfin_form("mu"), "mu"))
+        self._fill(Mu, self._assemble(self.get_dolfin_form("mu"), "mu"))
 
     def fp(self, Fp):
-        Fp.set_csr(self._assemble(self.get_dolfin_form("fp"), "fp"))
+        self._fill(Fp, self._assemble(self.get_dolfin_form("fp"), "fp"))
 
     def kp(self, Kp):
-        Kp.set_csr(self._assemble(self.get_dolfin_form("kp"), "kp"))
+        self._fill(Kp, self._assemble(self.get_dolfin_form("kp"), "kp"))
 
     def gp(self, Bt):
         """Discrete pressure gradient with the velocity BC rows constrained (``bc.apply(Bt)``
         for every velocity BC, reference assembling.py:174-180)."""
         B = self._assemble(self.get_dolfin_form("gp"), "gp")
         dofs, _ = _bc_dofs_values(self._bcs)
-        Bt.set_csr(_dirichlet_rows(B, dofs) if dofs.size else B)
+        self._fill(Bt, _dirichlet_rows(B, dofs, self._row0()) if dofs.size else B)

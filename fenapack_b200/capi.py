@@ -18,10 +18,10 @@ _LIB_NAME = "libfenapack_cuda.so"
 _lib = None
 
 # operator ids (enum fnp_operator)
-MAT_A00, MAT_A01, MAT_A10, MAT_AP, MAT_MP, MAT_KP, MAT_P00 = range(7)
+MAT_A00, MAT_A01, MAT_A10, MAT_AP, MAT_MP, MAT_KP, MAT_P00, MAT_P01, MAT_A11 = range(9)
 MAT_RP = 100      # derived operator of the PCDR variants (introspection / spmv only)
 MAT_NAMES = {"A00": MAT_A00, "A01": MAT_A01, "A10": MAT_A10, "Ap": MAT_AP, "Mp": MAT_MP,
-             "Kp": MAT_KP, "P00": MAT_P00}
+             "Kp": MAT_KP, "P00": MAT_P00, "P01": MAT_P01, "A11": MAT_A11}
 
 ERR_ARG, ERR_CUDA, ERR_OPTION, ERR_NCCL, ERR_STATE, ERR_NUMERIC = -1, -2, -3, -4, -5, -6
 
@@ -57,6 +57,7 @@ SIGNATURES = {
     "fnp_solve": (C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int, _c_int32_p, _c_double_p, _c_int32_p]),
     "fnp_solve_monolithic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _c_int32_p,
                                        _c_double_p, _c_int32_p]),
+    "fnp_get_converged_reason": (C.c_int, [C.c_void_p, _c_int32_p]),
     "fnp_get_residual_history": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "fnp_operator_block_size": (C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
     "fnp_amg_num_levels": (C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
@@ -294,6 +295,11 @@ class Context:
         _check(self._lib.fnp_solve(self._h, _ptr(b_u), _ptr(b_p), _ptr(x_u), _ptr(x_p), 1,
                                    C.byref(its), C.byref(rn), C.byref(nap)))
         return its.value, rn.value, nap.value
+
+    def converged_reason(self):
+        r = C.c_int32()
+        _check(self._lib.fnp_get_converged_reason(self._h, C.byref(r)))
+        return r.value
 
     def residual_history(self):
         buf = np.empty(20000)

@@ -191,10 +191,13 @@ static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, dou
   // With >= 2 smoothing steps the first Chebyshev iterate s D^-1 b is a by-product of the kernel that
   // produces b: the restriction of the level above (pre-smoothing) and the residual (post-smoothing)
   // write it into the smoother's first buffer, which saves two launches per level.
-  const bool fuse = p.smooth_steps >= 2;
+  // (Not on large levels: there the epilogue's extra loads and stores slow the gather-bound SpMV
+  // kernel by more than a streaming kernel of three vectors costs.)
+  auto fuses = [&](DevLevel &lv) { return p.smooth_steps >= 2 && lv.A().vec_rows() < 1500000; };
+  const bool fuse = fuses(L);
   auto first_step = [&](DevLevel &lv) {
     Jacobi1 j;
-    if (fuse) {
+    if (fuses(lv)) {
       j.y2 = lv.w0.p;
       j.d2 = lv.A().dinv.p;
       j.s2 = cheb_first_step_scale(lv.rho / p.eig_ratio, lv.rho);
@@ -213,7 +216,7 @@ static void vcycle_level(Ctx &c, DevHierarchy &H, size_t l, const double *b, dou
     DevLevel &C = H.levels[l + 1];
     const bool c_smooths = !(l + 2 == H.levels.size() && !H.tail);      // the coarsest level is solved, not smoothed
     spmv_store(c, L.R, L.r.p, C.b.p, c_smooths ? first_step(C) : Jacobi1());
-    vcycle_level(c, H, l + 1, C.b.p, C.x.p, c_smooths && fuse);
+    vcycle_level(c, H, l + 1, C.b.p, C.x.p, c_smooths && fuses(C));
     xc = C.x.p;
   }
   // x += P x_c

@@ -643,6 +643,12 @@ int fnp_solve_monolithic(fnp_context *ctx, const double *b, double *x, int on_de
   FNP_API_END
 }
 
+int fnp_get_converged_reason(fnp_context *ctx, int32_t *reason) {
+  if (!ctx || !reason) return FNP_ERR_ARG;
+  *reason = ctx->c.converged_reason;
+  return FNP_OK;
+}
+
 int fnp_get_residual_history(fnp_context *ctx, double *out, int32_t capacity) {
   if (!ctx || !out) return FNP_ERR_ARG;
   const auto &h = ctx->c.res_hist;

@@ -407,7 +407,7 @@ struct Ctx {
   DevCsr rp;
   DevHierarchy amg_rp;
   int spmv_mode = 0;            // 0 auto (by row-length histogram), 1 CSR vector kernel always, 2 SELL always
-  int sell_gather = 95;         // SpMV kernel variant bits (kernels.cu): 1 wide gathers, 2 six CTAs/SM, 4 L2 prefetch, 8 wide epilogue (SELL);
+  int sell_gather = 79;         // SpMV kernel variant bits (kernels.cu): 1 wide gathers, 2 six CTAs/SM, 4 L2 prefetch, 8 wide epilogue (SELL);
                                 // 16 L2 prefetch in the CSR sub-warp kernel (experimental)
   int sell_sigma = 1024;        // SELL sorting window (rows)
   int64_t refresh_chunk_terms = (int64_t)1 << 30;   // Galerkin refresh plan: terms per device chunk (option fnp_refresh_chunk_terms)
@@ -435,7 +435,7 @@ struct Ctx {
   DevBuf<double> stage_vals;                         // staging of host value arrays (persistent)
   DevBuf<int> d_flag;                                // error / decision word of the ingest kernels
   int pattern_gen[FNP_MAT_COUNT] = {};               // bumped whenever the stored pattern of an operator is rebuilt
-  int kron_bs[FNP_MAT_COUNT] = {1, 1, 1, 1, 1, 1, 1};
+  int kron_bs[FNP_MAT_COUNT] = {1, 1, 1, 1, 1, 1, 1, 1, 1};
   std::vector<int32_t> kron_rowptr[FNP_MAT_COUNT];  // row pointers of the expanded (user) pattern, for value checks
   bool have_pattern[FNP_MAT_COUNT] = {};
   bool have_values[FNP_MAT_COUNT] = {};

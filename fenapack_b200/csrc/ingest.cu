@@ -26,12 +26,12 @@ std::shared_ptr<HaloPlan> build_halo(Ctx &c, HostCsr &h, const std::vector<int64
                                      std::vector<int64_t> *ghost_global_out);
 std::shared_ptr<HaloPlan> expand_plan(Ctx &c, const HaloPlan &p, int bs);
 
-static const char *kNames[FNP_MAT_COUNT] = {"A00", "A01", "A10", "Ap", "Mp", "Kp", "P00"};
+static const char *kNames[FNP_MAT_COUNT] = {"A00", "A01", "A10", "Ap", "Mp", "Kp", "P00", "P01", "A11"};
 
 static void op_shape(const Ctx &c, int which, int64_t &nrows, int64_t &ncols) {
   switch (which) {
     case FNP_MAT_A00: case FNP_MAT_P00: nrows = c.n_u; ncols = c.n_u_global; break;
-    case FNP_MAT_A01: nrows = c.n_u; ncols = c.n_p_global; break;
+    case FNP_MAT_A01: case FNP_MAT_P01: nrows = c.n_u; ncols = c.n_p_global; break;
     case FNP_MAT_A10: nrows = c.n_p; ncols = c.n_u_global; break;
     default: nrows = c.n_p; ncols = c.n_p_global; break;
   }

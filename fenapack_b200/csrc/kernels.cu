@@ -102,7 +102,8 @@ __device__ __forceinline__ void gather3_wide(const double *__restrict__ p, doubl
   a2 = odd ? hi.y : hi.x;
 }
 
-// PF (option fnp_sell_gather bit 16; round 2: A10 0.140 -> 0.119 ms isolated): lane 0 of every warp pulls the
+// PF (option fnp_sell_gather bit 16, off by default; round 2: A10 0.140 -> 0.119 ms in isolation but
+// 123 -> 142 us inside the solve): lane 0 of every warp pulls the
 // contiguous (col, val) range of the warp's 32 / LANES rows into L2 with two bulk prefetches, as the
 // SELL kernel does for its slice (the ends are trimmed to 16-byte boundaries: a prefetch is a hint).
 template <int LANES, int BS, class Epi, bool PF>
@@ -453,10 +454,12 @@ spmv_sell_mw_kernel(int nslices, const int32_t *__restrict__ sl_ptr, const int32
 }
 
 // warps per slice of the multi-warp kernel: enough threads to fill the GPU (~600 k), at least
-// ~6 entries per lane
+// ~10 entries per lane.  Measured (round 2, 64^3 cavity): level 1 of the velocity hierarchy (207 k
+// rows x 51) 99.7 -> 73.6 us and level 2 33.9 -> 14.0 us with 4 warps; two warps on the 15-entry rows of
+// Ap / Mp were slower (15.3 -> 17.1 us), and so was the kernel on operators above a million rows.
 static int pick_sell_warps(int64_t nrows, double mean_row, int64_t target_threads) {
   int t = 1;
-  while (t < 8 && nrows * t < target_threads && mean_row / (2 * t) >= 6.0) t *= 2;
+  while (t < 8 && nrows * t < target_threads && mean_row / (2 * t) >= 10.0) t *= 2;
   return t;
 }
 
@@ -646,6 +649,12 @@ void csr_set_values(Ctx &c, DevCsr &A, const HostCsr &h, const double *val, bool
   FNP_CUDA(cudaStreamSynchronize(c.stream));
 }
 
+// vectors of the fused epilogue that move besides y (written once) and x (read once), which
+// DevCsr::spmv_bytes counts: the algorithmic traffic of the fused operation as implemented
+static inline int epi_extra_vectors(const EpiStore &e) { return e.y2 ? 2 : 0; }
+static inline int epi_extra_vectors(const EpiAxpby &e) { return 1 + (e.y2 ? 2 : 0); }
+static inline int epi_extra_vectors(const EpiCheb &e) { return 2 + (e.p0 ? 1 : 0) + (e.add ? 1 : 0); }
+
 template <int BS, class Epi>
 static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &epi) {
   const double *xg = nullptr;
@@ -660,7 +669,7 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
   // peer-memory exchange: the kernel that reads ghosts waits for the neighbours' flags itself and
   // derives the ghost slot from the device-resident sequence number (graph replayable)
   const HaloWaitDev *hw_ghost = (A.halo && A.halo->p2p && A.halo->nghost > 0) ? A.halo->d_wait.p : nullptr;
-  StageTimer kt(c, "spmv " + A.tag, 2, A.spmv_bytes());
+  StageTimer kt(c, "spmv " + A.tag, 2, A.spmv_bytes() + 8.0 * (double)A.vec_rows() * epi_extra_vectors(epi));
   if (A.sell) {
     auto launch = [&](int nsl, const int32_t *ptr, const int32_t *perm, int64_t off, const HaloWaitDev *hw) {
       if (nsl <= 0) return;

@@ -170,8 +170,10 @@ void pc_apply(Ctx &c, const double *x_u, const double *x_p, double *y_u, double 
   // t = x_u - A01 y_p
   double *tu = c.u_w[0].p;
   {
+    // the triangular apply uses the block of the preconditioning matrix (PCFIELDSPLIT, useAmat = false)
     StageTimer t2(c, "FENaPack: A01 mult");
-    spmv_axpby(c, c.dmat[FNP_MAT_A01], y_p, -1.0, 1.0, x_u, tu);
+    const DevCsr &B01 = c.have_values[FNP_MAT_P01] ? c.dmat[FNP_MAT_P01] : c.dmat[FNP_MAT_A01];
+    spmv_axpby(c, B01, y_p, -1.0, 1.0, x_u, tu);
   }
   // y_u = A00^-1 t
   u_solve(c, tu, y_u);
@@ -225,6 +227,7 @@ void system_matvec(Ctx &c, const double *x, double *y) {
   spmv_store(c, c.dmat[FNP_MAT_A00], xu, yu);
   spmv_axpby(c, c.dmat[FNP_MAT_A01], xp, 1.0, 1.0, yu, yu);
   spmv_store(c, c.dmat[FNP_MAT_A10], xu, yp);
+  if (c.have_values[FNP_MAT_A11]) spmv_axpby(c, c.dmat[FNP_MAT_A11], xp, 1.0, 1.0, yp, yp);
 }
 
 // ---------------------------------------------------------------------------
@@ -241,6 +244,101 @@ static void build_amg(Ctx &c, int which, DevHierarchy &H, const AmgParams &p) {
   amg_build_host(c, c.hmat[which], begins, p, H.host);
   amg_upload(c, H, which == FNP_MAT_AP ? "Ap" : "A00", &c.dmat[which], bs);
   H.host_vals_stale = false;
+}
+
+std::vector<double> comm_allgather_padded(Ctx &c, const double *v, int64_t count, int64_t maxcount);
+double comm_allreduce(Ctx &c, double v, bool max_op);
+std::shared_ptr<HaloPlan> build_halo(Ctx &c, HostCsr &h, const std::vector<int64_t> &begins,
+                                     std::vector<int64_t> *ghost_global_out);
+
+// Rp = Bt^T diag(Mu)^-1 Bt, row partitioned like every pressure operator.  A rank holds the u-rows of
+// Bt, so its product T_r = Bt_r^T D_r^-1 Bt_r contributes to rows of Rp owned by its neighbours (the
+// transposeMatMult of the reference, field_split_backend.py:161-166, which PETSc resolves with its own
+// communication): the foreign rows travel as (row, column, value) triplets in one padded all-gather
+// and every rank adds what falls into its range, own contribution first, then by rank -- a fixed order.
+static void build_rp(Ctx &c) {
+  const HostCsr &Bt = c.hmat[FNP_MAT_A01];     // local u rows, GLOBAL p columns
+  HostCsr S = Bt, B, T;                        // S = D^-1 Bt (rows scaled), B = Bt^T
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < S.nrows; ++i) {
+    const double m = c.mu_diag[i];
+    const double f = m != 0.0 ? 1.0 / m : 0.0;
+    for (int32_t k = S.rowptr[i]; k < S.rowptr[i + 1]; ++k) S.val[k] *= f;
+  }
+  host_transpose(Bt, B);                       // n_p_global x n_u_local
+  host_spgemm(B, S, T);                        // n_p_global x n_p_global, rows sorted by column
+  const int64_t p0 = c.p_begin, p1 = c.p_begin + c.n_p;
+  HostCsr &R = c.h_rp;
+  if (c.nranks == 1) {
+    R = std::move(T);
+  } else {
+    std::vector<double> mine;                  // foreign rows as triplets
+    for (int64_t i = 0; i < T.nrows; ++i) {
+      if (i >= p0 && i < p1) continue;
+      for (int32_t k = T.rowptr[i]; k < T.rowptr[i + 1]; ++k) {
+        mine.push_back((double)i);
+        mine.push_back((double)T.col[k]);
+        mine.push_back(T.val[k]);
+      }
+    }
+    const int64_t cnt = (int64_t)mine.size();
+    const int64_t maxcnt = std::max<int64_t>(3, (int64_t)comm_allreduce(c, (double)cnt, true));
+    const double marker = -1.0;                // padding: row id -1
+    mine.resize((size_t)maxcnt, marker);
+    for (int64_t t = cnt; t < maxcnt; ++t) mine[(size_t)t] = marker;
+    std::vector<double> all = comm_allgather_padded(c, mine.data(), maxcnt, maxcnt);
+    // own rows first, then the neighbours' contributions in rank order
+    std::vector<std::vector<std::pair<int32_t, double>>> rows((size_t)c.n_p);
+    for (int64_t i = p0; i < p1; ++i)
+      for (int32_t k = T.rowptr[i]; k < T.rowptr[i + 1]; ++k) rows[(size_t)(i - p0)].push_back({T.col[k], T.val[k]});
+    for (int q = 0; q < c.nranks; ++q) {
+      if (q == c.rank) continue;
+      const double *tq = all.data() + (size_t)q * maxcnt;
+      for (int64_t t = 0; t + 2 < maxcnt; t += 3) {
+        const int64_t i = (int64_t)tq[t];
+        if (i < p0 || i >= p1) continue;
+        rows[(size_t)(i - p0)].push_back({(int32_t)tq[t + 1], tq[t + 2]});
+      }
+    }
+    R = HostCsr();
+    R.nrows = c.n_p;
+    R.ncols = c.n_p_global;
+    R.rowptr.assign((size_t)c.n_p + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < c.n_p; ++i) {
+      auto &r = rows[(size_t)i];
+      std::stable_sort(r.begin(), r.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+      size_t o = 0;
+      for (size_t t = 0; t < r.size(); ++t) {
+        if (o > 0 && r[o - 1].first == r[t].first) r[o - 1].second += r[t].second;
+        else r[o++] = r[t];
+      }
+      r.resize(o);
+    }
+    for (int64_t i = 0; i < c.n_p; ++i) R.rowptr[(size_t)i + 1] = R.rowptr[(size_t)i] + (int32_t)rows[(size_t)i].size();
+    R.col.resize((size_t)R.rowptr[(size_t)c.n_p]);
+    R.val.resize((size_t)R.rowptr[(size_t)c.n_p]);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < c.n_p; ++i) {
+      int32_t o = R.rowptr[(size_t)i];
+      for (const auto &e : rows[(size_t)i]) {
+        R.col[(size_t)o] = e.first;
+        R.val[(size_t)o] = e.second;
+        ++o;
+      }
+    }
+  }
+  // device copy: local column numbering [owned | ghost] and a halo plan, like the uploaded operators
+  HostCsr loc = R;
+  std::shared_ptr<HaloPlan> plan = build_halo(c, loc, c.p_begins, nullptr);
+  const int64_t n_own = c.n_p;
+  csr_upload_pattern(c, c.rp, loc, "Rp", (plan && (c.overlap || c.p2p)) ? n_own : -1, 1, plan ? n_own : -1);
+  c.rp.halo = plan;
+  if (plan) {
+    c.rp.ncols_own = (int32_t)n_own;
+    c.rp.nghost = plan->nghost;
+  }
+  csr_set_values(c, c.rp, loc, R.val.data(), true);
 }
 
 void setup_all(Ctx &c) {
@@ -298,24 +396,12 @@ void setup_all(Ctx &c) {
   if (c.variant >= 3) {
     // PCDR: Rp = Bt^T diag(Mu)^-1 Bt with Bt = A01 (PCDInterface._build_approx_Ap,
     // field_split_backend.py:142-166), rebuilt when A01 or Mu changed
-    FNP_REQUIRE(c.nranks == 1, FNP_ERR_STATE, "the PCDR variants are single-rank so far");
     FNP_REQUIRE(c.have_values[FNP_MAT_A01] && (int64_t)c.mu_diag.size() == c.n_u, FNP_ERR_STATE,
                 "PCDR needs A01 (the discrete pressure gradient) and fnp_set_mu_diag");
     if (c.dirty[FNP_MAT_A01] || c.mu_dirty || !c.amg_rp.built) {
       ensure_host_values(c, FNP_MAT_A01);
       c.drop_graph();
-      const HostCsr &Bt = c.hmat[FNP_MAT_A01];
-      HostCsr S = Bt, B;                        // S = D^-1 Bt (rows scaled), B = Bt^T
-#pragma omp parallel for schedule(static)
-      for (int64_t i = 0; i < S.nrows; ++i) {
-        const double m = c.mu_diag[i];
-        const double f = m != 0.0 ? 1.0 / m : 0.0;
-        for (int32_t k = S.rowptr[i]; k < S.rowptr[i + 1]; ++k) S.val[k] *= f;
-      }
-      host_transpose(Bt, B);
-      host_spgemm(B, S, c.h_rp);
-      csr_upload_pattern(c, c.rp, c.h_rp, "Rp");
-      csr_set_values(c, c.rp, c.h_rp, c.h_rp.val.data(), true);
+      build_rp(c);
       if (c.opt_rp.pc == PC_AMG) {
         c.amg_rp.params = c.opt_rp.amg;
         amg_build_host(c, c.h_rp, c.p_begins, c.opt_rp.amg, c.amg_rp.host);

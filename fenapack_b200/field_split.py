@@ -17,11 +17,13 @@ per-apply compatibility mode described in INTEGRATION.md.
 from __future__ import annotations
 
 import importlib
+import os
 
 import numpy as np
 
 from . import capi
-from ._backend import PETSc
+from ._backend import PETSc, mat_state
+from ._comm import HostComm
 from .field_split_backend import PCDInterface
 from .preconditioners import BasePCDPC, PCDPC_BRM1
 from .utils import allow_only_one_call
@@ -32,9 +34,10 @@ _U_KEYS = ("ksp_type", "ksp_max_it", "pc_type", "pc_hypre_type", "pc_amg_thresho
            "pc_amg_refresh")
 
 
-def dofmap_dofs_is(dofmap):
-    """Index set of the dofs owned by a sub-space (reference _field_split_utils.py:39-50)."""
-    return PETSc.IS(np.asarray(dofmap.dofs(), dtype=np.int64))
+def dofmap_dofs_is(dofmap, comm=None):
+    """Index set of the dofs owned by a sub-space (reference _field_split_utils.py:39-50):
+    ``dofmap.dofs()`` lists the OWNED dofs of this rank in the global monolithic numbering."""
+    return PETSc.IS(np.asarray(dofmap.dofs(), dtype=np.int64), comm)
 
 
 class _SubPC(object):
@@ -60,8 +63,15 @@ class PCDKSP(object):
     """GMRES with right fieldsplit preconditioning using upper Schur factorization
     and PCD Schur complement approximation, solved on the GPU."""
 
-    def __init__(self, comm=None, device=0):
+    def __init__(self, comm=None, device=None):
+        """``comm``: the communicator of the solver (reference field_split.py:46): every rank owns a
+        contiguous range of the monolithic numbering, drives one GPU, and the ranks' device contexts
+        are joined through NCCL (``fnp_create_dist``).  ``device``: CUDA device of this rank (default:
+        ``LOCAL_RANK`` of the launcher, else the rank)."""
         self.comm = comm if comm is not None else PETSc.COMM_WORLD
+        self._hc = HostComm(self.comm)
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", self._hc.rank)) if self._hc.size > 1 else 0
         self._device = device
         self._prefix = ""
         self._A = self._P = None
@@ -131,17 +141,32 @@ class PCDKSP(object):
         if self._A is None:
             raise RuntimeError("init_pcd: setOperators must be called first")
         V = pcd_assembler.function_space()
-        is0 = dofmap_dofs_is(V.sub(0).dofmap())
-        is1 = dofmap_dofs_is(V.sub(1).dofmap())
+        is0 = dofmap_dofs_is(V.sub(0).dofmap(), self.comm)
+        is1 = dofmap_dofs_is(V.sub(1).dofmap(), self.comm)
         self.is_u, self.is_p = is0, is1
         # From now on forbid setting options prefix
         self.setOptionsPrefix = self._forbid_setOptionsPrefix
         self.setFromOptions()
 
-        # device context owning the whole block-triangular apply
-        ctx = capi.Context(self._device)
-        ctx.set_layout(is0.getSize(), is1.getSize())
-        ctx.set_index_sets(is0.getIndices(), is1.getIndices())
+        # device context owning the whole block-triangular apply; one per rank, joined through
+        # NCCL when the communicator has several ranks (the unique id travels over the caller's
+        # communicator, as the reference's sub-solvers inherit ``comm``, field_split.py:75-77)
+        hc = self._hc
+        if hc.size > 1:
+            uid = hc.bcast(capi.nccl_unique_id() if hc.rank == 0 else None, root=0)
+            ctx = capi.Context(self._device, nccl_id=uid, rank=hc.rank, nranks=hc.size)
+        else:
+            ctx = capi.Context(self._device)
+        # ownership ranges of the two split numberings: position in the owned index set plus the
+        # exclusive scan of the local sizes (SubfieldBC.h:138-140)
+        n_u, n_p = is0.getLocalSize(), is1.getLocalSize()
+        u_begin, p_begin = hc.exscan(n_u), hc.exscan(n_p)
+        ctx.set_layout(n_u, n_p, u_begin, hc.allreduce(n_u), p_begin, hc.allreduce(n_p))
+        rstart = self._A.getOwnershipRange()[0] if hasattr(self._A, "getOwnershipRange") else 0
+        if np.any(is0.getIndices() < rstart) or np.any(is1.getIndices() < rstart) or \
+                is0.getLocalSize() + is1.getLocalSize() != self._local_size():
+            raise RuntimeError("PCDKSP.init_pcd: the sub-space index sets do not partition this rank's rows of the operator")
+        ctx.set_index_sets(is0.getIndices() - rstart, is1.getIndices() - rstart)
         self._ctx = ctx
 
         # PCD PC class: option > argument > default (field_split.py:109-124)
@@ -176,29 +201,65 @@ class PCDKSP(object):
         self._setup()
 
     # -- set-up / value refresh -------------------------------
+    def _local_size(self):
+        A = self._A
+        if hasattr(A, "getLocalSize"):
+            return A.getLocalSize()[0]
+        return A.getSize()[0]
+
     def _blocks(self):
+        """The blocks PCFIELDSPLIT works with.  The Krylov MatMult uses the system matrix A in full
+        (A00, A01, A10 and, for pressure-stabilised discretisations, A11); the triangular apply cuts
+        its blocks from the preconditioning matrix P (PETSc's default useAmat = false): P00 for the
+        velocity solve and P01 for the coupling -- uploaded separately only when they differ from A's."""
         A, P = self._A, self._P
         out = {capi.MAT_A00: A.createSubMatrix(self.is_u, self.is_u),
-               capi.MAT_A01: P.createSubMatrix(self.is_u, self.is_p),
+               capi.MAT_A01: A.createSubMatrix(self.is_u, self.is_p),
                capi.MAT_A10: A.createSubMatrix(self.is_p, self.is_u)}
+        a11 = A.createSubMatrix(self.is_p, self.is_p)
+        a11_nonzero = bool(np.any(a11.getValuesCSR()[2] != 0.0))
+        if self._hc.allreduce(1 if a11_nonzero else 0) or getattr(self, "_has_a11", False):
+            out[capi.MAT_A11] = a11
+            self._has_a11 = True
         if P is not A:
             out[capi.MAT_P00] = P.createSubMatrix(self.is_u, self.is_u)
+            p01 = P.createSubMatrix(self.is_u, self.is_p)
+            ia, ja, va = out[capi.MAT_A01].getValuesCSR()
+            ip, jp, vp = p01.getValuesCSR()
+            differs = not (np.array_equal(ia, ip) and np.array_equal(ja, jp) and np.array_equal(va, vp))
+            if self._hc.allreduce(1 if differs else 0) or getattr(self, "_has_p01", False):
+                out[capi.MAT_P01] = p01
+                self._has_p01 = True
         return out
 
     def _operator_state(self):
-        return (getattr(self._A, "state", None), getattr(self._P, "state", None))
+        return (mat_state(self._A), mat_state(self._P))
 
     def _setup(self):
-        """PCSetUp chain: (re-)extract the blocks of the in-place re-assembled
-        operators -- pattern once, values every time -- then the python PC's setUp."""
+        """PCSetUp chain: (re-)extract the blocks of the in-place re-assembled operators -- pattern
+        once, values whenever they changed -- then the python PC's setUp.  A00 / P00 change with
+        every Newton or time step; the coupling blocks normally do not, but are compared and
+        re-uploaded when they do (e.g. SUPG pressure terms), never silently kept."""
         ctx = self._ctx
         first = not self._setup_done
+        if first:
+            self._uploaded = {}
         for which, mat in self._blocks().items():
             indptr, indices, data = mat.getValuesCSR()
-            if first:
+            if which not in self._uploaded:
+                if not first:
+                    raise RuntimeError("PCDKSP: block %d of the operators appeared after init_pcd "
+                                       "(its pattern was empty at the first set-up)" % which)
                 ctx.set_pattern(which, indptr, indices)
-            if first or which in (capi.MAT_A00, capi.MAT_P00):
                 ctx.set_values(which, data)
+                self._uploaded[which] = None if which in (capi.MAT_A00, capi.MAT_P00) else np.array(data, copy=True)
+            elif which in (capi.MAT_A00, capi.MAT_P00):
+                ctx.set_values(which, data)
+            else:
+                changed = self._hc.allreduce(0 if np.array_equal(self._uploaded[which], data) else 1)
+                if changed:
+                    ctx.set_values(which, data)
+                    self._uploaded[which] = np.array(data, copy=True)
         self._pcd_pc.setUp(self._sub_pc)
         ctx.setup()
         self._state = self._operator_state()
@@ -215,9 +276,7 @@ class PCDKSP(object):
         xa = x.getArray() if hasattr(x, "getArray") else x
         xa[:] = sol
         self._its, self._rnorm = its, rn
-        hist = self._ctx.residual_history()
-        rtol = float(self._outer_opts.get("ksp_rtol", 1e-5 if False else 1e-6))
-        self._reason = 2 if (len(hist) and rn <= max(rtol * hist[0], 1e-50)) else -3
+        self._reason = self._ctx.converged_reason()       # KSPConvergedReason from the library (rtol 2, atol 3, its -3)
         return its
 
     def getIterationNumber(self):

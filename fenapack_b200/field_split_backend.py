@@ -53,6 +53,15 @@ class PCDInterface(object):
             self._subbcs = (np.asarray(idx, dtype=np.int32), np.asarray(vals, dtype=np.float64))
         return self._subbcs
 
+    def pcd_bc_indices_global(self, comm=None):
+        """The same index list in the GLOBAL numbering of the "p" split vector: local position plus
+        the exclusive scan of the owned sizes over the ranks (SubfieldBC.h:138-140) -- what the
+        reference hands to VecSetValues."""
+        from ._comm import HostComm
+        idx, vals = self.pcd_bc_indices()
+        hc = HostComm(comm if comm is not None else self.is_p.comm)
+        return idx.astype(np.int64) + hc.exscan(self.is_p.getLocalSize()), vals
+
     def apply_pcd_bcs(self, vec):
         """Apply bcs to an intermediate pressure vector of PCD pc (host-side
         equivalent of SubfieldBC::apply; the device path does this itself)."""
@@ -63,7 +72,7 @@ class PCDInterface(object):
     def _work_mat(self, key):
         m = self.scratch.get(key)
         if m is None:
-            m = self.scratch[key] = PETSc.Mat()
+            m = self.scratch[key] = PETSc.Mat(comm=getattr(self.is_p, "comm", None))
         return m
 
     def _assemble_operator_deep(self, key, assemble_func, isrow, iscol=None, submat=None):

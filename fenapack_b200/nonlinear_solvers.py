@@ -59,9 +59,11 @@ class PCDNewtonSolver(object):
         """Solve F(x) = 0.  Returns (iterations, converged)."""
         self._problem = problem
         prm = self.parameters
-        n = x.getSize()
-        b = PETSc.Vec(np.zeros(n))
-        dx = PETSc.Vec(np.zeros(n))
+        n = x.getLocalSize()
+        comm = getattr(x, "comm", None)
+        b = PETSc.Vec(np.zeros(n), comm)
+        dx = PETSc.Vec(np.zeros(n), comm)
+        self._A.comm = self._P.comm = comm if comm is not None else self._A.comm
         problem.F(b, x)
         r0 = b.norm()
         converged = r0 <= prm["absolute_tolerance"]

@@ -99,6 +99,9 @@ class BasePCDPC(object):
 
     def _ensure_ctx(self, n_p):
         if self._ctx is None:
+            if getattr(getattr(self.interface.is_p, "comm", None), "size", 1) > 1:
+                raise RuntimeError("stand-alone python-PC mode is single rank; multi-rank runs go through PCDKSP, "
+                                   "which attaches its distributed device context")
             self._ctx = capi.Context(self.interface.device if hasattr(self.interface, "device") else 0)
             self._ctx.set_options(self._device_opts)
             self._ctx.set_layout(0, n_p)
@@ -117,7 +120,7 @@ class BasePCDPC(object):
         if Kp is not None:        # updated only if not constant
             self.mat_Kp = Kp
             self.mat_Kp.setOptionsPrefix(self._pc_prefix + "PCD_Kp_")
-        n_p = self.mat_Mp.getSize()[0]
+        n_p = self.mat_Mp.getLocalSize()[0] if hasattr(self.mat_Mp, "getLocalSize") else self.mat_Mp.getSize()[0]
         self._ensure_ctx(n_p)
         ctx = self._ctx
         ctx.set_option("fieldsplit_p_pc_python_type", self._variant_name())

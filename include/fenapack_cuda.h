@@ -55,7 +55,12 @@ enum fnp_operator {
   FNP_MAT_KP = 5,  /* pressure convection (+reaction) matrix       field_split_backend.py:79-83 */
   FNP_MAT_P00 = 6, /* optional preconditioning velocity block (stabilised a_pc,
                       nonlinear_solvers.py:75-76); defaults to A00 */
-  FNP_MAT_COUNT = 7,
+  FNP_MAT_P01 = 7, /* optional u-rows x p-cols block of the PRECONDITIONING matrix: PCFIELDSPLIT cuts the
+                      blocks of its triangular apply from Pmat (useAmat = false), the Krylov MatMult uses
+                      Amat; set it only when the two differ.  Defaults to A01 */
+  FNP_MAT_A11 = 8, /* optional p-rows x p-cols block of the system matrix (zero for Taylor-Hood; non-zero
+                      for pressure-stabilised discretisations).  Enters the Krylov MatMult only */
+  FNP_MAT_COUNT = 9,
   FNP_MAT_RP = 100 /* derived (PCDR): Rp = Bt^T diag(Mu)^-1 Bt, built by fnp_setup; valid for
                       fnp_spmv and the AMG introspection calls only */
 };
@@ -108,7 +113,9 @@ int fnp_synchronize(fnp_context *ctx);
  * auto|csr|sell, fnp_sell_max_mean_row, fnp_sell_sigma (sorting window, before fnp_set_pattern),
  * fnp_sell_gather (bit mask: 1 16-byte gathers, 2 six CTAs/SM, 4 L2 bulk prefetch, 8 16-byte epilogue
  * loads, 16 L2 bulk prefetch in the CSR kernel, 64 default instead of evict-first cache policy for
- * operators of at most 64 MB; default 95 = all, results are bit-identical for every value),
+ * operators of at most 64 MB; default 79, results are bit-identical for every value),
+ * fnp_sell_warps (warps per SELL slice, 0 = from rows x mean row), fnp_sell_warps_rows, fnp_gmres_sync,
+ * fnp_refresh_chunk_terms,
  * fnp_kronecker, fnp_prune_zeros, fnp_halo_overlap, fnp_halo_p2p. */
 int fnp_set_option(fnp_context *ctx, const char *name, const char *value);
 
@@ -190,6 +197,12 @@ int fnp_solve(fnp_context *ctx, const double *b_u, const double *b_p, double *x_
 /* Same with monolithic local vectors (needs fnp_set_index_sets). */
 int fnp_solve_monolithic(fnp_context *ctx, const double *b, double *x, int on_device,
                          int32_t *iterations, double *residual_norm, int32_t *pc_applies);
+
+/* KSPConvergedReason of the last fnp_solve[_monolithic], with PETSc's codes (KSPConvergedDefault on
+ * the recurrence estimate): 2 KSP_CONVERGED_RTOL, 3 KSP_CONVERGED_ATOL, -3 KSP_DIVERGED_ITS; 0 before
+ * the first solve.  What PCDKrylovSolver.solve checks through dolfin.PETScKrylovSolver
+ * (field_split.py:153-187). */
+int fnp_get_converged_reason(fnp_context *ctx, int32_t *reason);
 
 /* Residual history of the last fnp_solve (entry 0 = ||b||). Returns count copied. */
 int fnp_get_residual_history(fnp_context *ctx, double *out, int32_t capacity);

@@ -274,19 +274,22 @@ def build_hierarchy(A, theta=0.08, max_levels=12, coarse_size=400, smooth_steps=
     return H
 
 
-def build_hierarchy_kron(A, bs=1, blocks=None, **kw):
+def build_hierarchy_kron(A, bs=1, blocks=None, S=None, **kw):
     """Hierarchy of A = S (x) I_bs (interleaved components) arranged the way the
     library does it in Kronecker mode: the scalar operator S is coarsened (node blocks
-    for a multi-rank partition) and every level is expanded back to the full block."""
+    for a multi-rank partition) and every level is expanded back to the full block.
+    `S` may be handed in (large systems: extracting it from A and expanding level 0 again
+    would only cost memory); level 0 then is A itself."""
     A = sp.csr_matrix(A)
     if bs == 1:
         return build_hierarchy(A, blocks=blocks, **kw)
-    S = A[::bs, :][:, ::bs].tocsr()
+    given = S is not None
+    S = sp.csr_matrix(S) if given else A[::bs, :][:, ::bs].tocsr()
     Hs = build_hierarchy(S, blocks=None if blocks is None else [b // bs for b in blocks], **kw)
     eye = sp.identity(bs, format="csr")
     H = Hierarchy(smooth_steps=Hs.smooth_steps, eig_ratio=Hs.eig_ratio)
-    for l in Hs.levels:
-        H.levels.append(Level(A=sp.kron(l.A, eye, format="csr"), dinv=np.repeat(l.dinv, bs), rho=l.rho,
+    for k, l in enumerate(Hs.levels):
+        H.levels.append(Level(A=A if (given and k == 0) else sp.kron(l.A, eye, format="csr"), dinv=np.repeat(l.dinv, bs), rho=l.rho,
                               P=None if l.P is None else sp.kron(l.P, eye, format="csr"),
                               R=None if l.R is None else sp.kron(l.R, eye, format="csr")))
     H.coarse_inv = np.kron(Hs.coarse_inv, np.eye(bs))

@@ -24,12 +24,23 @@ def split(n, world, align=1):
     return b
 
 
-def parity_check(rank, world, local, variant="BRM1", extra_options=None, p2p=None, repl=0):
+def parity_check(rank, world, local, variant="BRM1", extra_options=None, p2p=None, repl=0, pcdr=False):
     """Row-partitioned library against the serial oracle on a small problem.  Collective over
     torch.distributed (already initialised).  Returns the measured discrepancies; raises on a
-    violated tolerance."""
-    prob, _ = problems.channel(12, 4, 6, variant=variant) if variant == "BRM1" else problems.lid_driven_cavity(8, dim=3, variant="BRM2")
-    ub, pb = split(prob.n_u, world, 3), split(prob.n_p, world)
+    violated tolerance.  pcdr: the PCDR variant on the unsteady BFS problem (Rp = Bt^T D^-1 Bt is
+    assembled across the ranks)."""
+    dim = 3
+    if pcdr:
+        dim = 2
+        p0_, _ = problems.backward_facing_step(3, variant=variant, idt=5.0)
+        x0 = pa.direct_solver(p0_.system_matrix())(p0_.rhs())
+        prob, _ = problems.backward_facing_step(3, variant=variant, wind=x0[:p0_.n_u].reshape(-1, 2), idt=5.0,
+                                                stabilise=True, pcdr=True)
+    elif variant == "BRM1":
+        prob, _ = problems.channel(12, 4, 6, variant=variant)
+    else:
+        prob, _ = problems.lid_driven_cavity(8, dim=3, variant="BRM2")
+    ub, pb = split(prob.n_u, world, dim), split(prob.n_p, world)
     u0, u1, p0, p1 = ub[rank], ub[rank + 1], pb[rank], pb[rank + 1]
 
     idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -38,7 +49,10 @@ def parity_check(rank, world, local, variant="BRM1", extra_options=None, p2p=Non
     dist.broadcast(idt, 0)
     ctx = capi.Context(local, nccl_id=idt.cpu().numpy().tobytes(), rank=rank, nranks=world)
     opts = dict(ITERATIVE_OPTIONS)
-    opts["fieldsplit_p_pc_python_type"] = "fenapack.PCDPC_" + prob.variant
+    opts["fieldsplit_p_pc_python_type"] = ("fenapack.PCDRPC_" if pcdr else "fenapack.PCDPC_") + prob.variant
+    if pcdr:        # demo_unsteady-navier-stokes-pcdr.py:167-170
+        opts.update({"fieldsplit_p_PCD_Rp_ksp_type": "richardson", "fieldsplit_p_PCD_Rp_ksp_max_it": 1,
+                     "fieldsplit_p_PCD_Rp_pc_type": "hypre", "fieldsplit_p_PCD_Rp_pc_hypre_type": "boomeramg"})
     opts["fieldsplit_p_PCD_Mp_ksp_chebyshev_eigenvalues"] = "%r, %r" % tuple(prob.cheb_bounds)
     opts.update(extra_options or {})
     ctx.set_options(opts)
@@ -57,6 +71,8 @@ def parity_check(rank, world, local, variant="BRM1", extra_options=None, p2p=Non
         ctx.set_matrix(which, A[r0:r1, :].tocsr())
     sel = (prob.bc_idx >= p0) & (prob.bc_idx < p1)
     ctx.set_bc(prob.bc_idx[sel] - p0, prob.bc_val[sel])
+    if pcdr:
+        ctx.set_mu_diag(prob.mu_diag[u0:u1])
     ctx.setup()
 
     out = {}
@@ -73,12 +89,20 @@ def parity_check(rank, world, local, variant="BRM1", extra_options=None, p2p=Non
     out["spmv_relerr"] = worst
     # the preconditioner against the oracle with the same block-local hierarchy
     bs = ctx.block_size(capi.MAT_P00 if prob.P00 is not None else capi.MAT_A00)
-    assert bs == 3, "the Picard velocity block should be recognised as S (x) I_3"
+    assert bs == dim, "the Picard velocity block should be recognised as S (x) I_d"
     kw = {k[len("fieldsplit_u_pc_amg_"):]: int(v) for k, v in opts.items() if k == "fieldsplit_u_pc_amg_coarse_size"}
     kwp = {k[len("fieldsplit_p_PCD_Ap_pc_amg_"):]: int(v) for k, v in opts.items() if k == "fieldsplit_p_PCD_Ap_pc_amg_coarse_size"}
     Hu = oracle_hierarchy_like_library(P00, bs=bs, blocks=ub, replicate_size=repl, **kw)
     Hp = oamg.build_hierarchy(prob.Ap, blocks=pb, replicate_size=repl, **kwp)
-    pc = pa.PCDPreconditioner(prob, "iterative", amg_u=Hu, amg_p=Hp)
+    if pcdr:
+        Rp = pa.build_rp(prob.A01, prob.mu_diag)
+        v = rng.standard_normal(prob.n_p)
+        out["rp_spmv_relerr"] = relerr(ctx.spmv(capi.MAT_RP, v[p0:p1], p1 - p0), (Rp @ v)[p0:p1])
+        assert out["rp_spmv_relerr"] <= 1e-12, ("Rp", out["rp_spmv_relerr"])
+        Hr = oamg.build_hierarchy(Rp, blocks=pb, replicate_size=repl)
+        pc = pa.PCDPreconditioner(prob, "iterative", amg_u=Hu, amg_p=Hp, pcdr=True, amg_r=Hr)
+    else:
+        pc = pa.PCDPreconditioner(prob, "iterative", amg_u=Hu, amg_p=Hp)
     b = rng.standard_normal(prob.n_p)
     out["ap_solve_relerr"] = relerr(ctx.ap_solve(b[p0:p1]), pc.solve_Ap(b)[p0:p1])
     assert out["ap_solve_relerr"] <= 1e-9, "ap_solve"
@@ -99,7 +123,8 @@ def parity_check(rank, world, local, variant="BRM1", extra_options=None, p2p=Non
     out["solution_relerr"] = relerr(np.concatenate([su, sp_]), xs)
     assert out["solution_relerr"] <= 1e-5
     out.update({"its": int(its), "oracle_its": int(its_ref), "ndofs": int(prob.n_u + prob.n_p),
-                "problem": "channel 12x4x6 BRM1" if variant == "BRM1" else "cavity 8^3 BRM2"})
+                "problem": ("unsteady BFS level 3 PCDR " + variant) if pcdr else
+                           ("channel 12x4x6 BRM1" if variant == "BRM1" else "cavity 8^3 BRM2")})
     # worst case over the ranks (each rank checked its own rows)
     t = torch.tensor([out[k] for k in ("spmv_relerr", "ap_solve_relerr", "u_solve_relerr", "pc_apply_relerr",
                                        "solution_relerr")], dtype=torch.float64, device="cuda")
@@ -117,7 +142,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     variant = sys.argv[1] if len(sys.argv) > 1 else "BRM1"
     out = parity_check(rank, world, local, variant, p2p=os.environ.get("FNP_P2P") or None,
-                       repl=int(os.environ.get("FNP_REPL", "0")))
+                       repl=int(os.environ.get("FNP_REPL", "0")), pcdr=os.environ.get("FNP_PCDR") == "1")
     dist.barrier()
     if rank == 0:
         print(f"DIST OK world={world} variant={variant} its={out['its']} oracle_its={out['oracle_its']} {out}")

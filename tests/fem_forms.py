@@ -176,3 +176,51 @@ class BFSModel:
             parts.append(-self.asm.p1_boundary_flux_mass(self.wind(), lambda x: np.isclose(x[:, 0], -1.0), 1.0 / self.nu))
         # structural P1 pattern, so that refreshes are value-only
         return self._embed_p(struct_add(*parts))
+
+
+# ---------------------------------------------------------------------------------------------
+# row-partitioned view of a model (multi-rank drop-in tests): every rank assembles the whole
+# tensor on the host (test harness only) and hands over its contiguous range of rows of the
+# monolithic numbering, the way DOLFIN's tensors arrive in an MPI run
+# ---------------------------------------------------------------------------------------------
+class _OwnedDofMap(_DofMap):
+    def __init__(self, dofs, rows):
+        super().__init__(dofs)
+        self._rows = rows
+
+    def ownership_range(self):
+        return self._rows
+
+
+class PartitionedSpace(MixedSpace):
+    def __init__(self, is_u, is_p, rows):
+        r0, r1 = rows
+        self._rows = rows
+        self._subs = (_Sub(is_u[(is_u >= r0) & (is_u < r1)]), _Sub(is_p[(is_p >= r0) & (is_p < r1)]))
+
+    def dofmap(self):
+        return _OwnedDofMap(np.arange(*self._rows), self._rows)
+
+
+class PartitionedModel:
+    """Rows [r0, r1) of every form of ``model`` (global column ids)."""
+
+    def __init__(self, model, rank, nranks):
+        self.m = model
+        N = model.N
+        self.rows = (N * rank // nranks, N * (rank + 1) // nranks)
+        self.W = PartitionedSpace(model.is_u, model.is_p, self.rows)
+        self.bc_pcd = model.bc_pcd                     # all constrained dofs, global ids
+
+    def _rows_of(self, f):
+        r0, r1 = self.rows
+
+        def g():
+            T = f()
+            return T[r0:r1] if isinstance(T, np.ndarray) else sp.csr_matrix(T)[r0:r1, :]
+        return g
+
+    def __getattr__(self, name):
+        if name in ("a", "L", "a_pc", "mp", "mu", "ap", "kp"):
+            return self._rows_of(getattr(self.m, name))
+        raise AttributeError(name)

@@ -7,6 +7,7 @@ import pytest
 import scipy.sparse.linalg as spla
 
 import fenapack_b200 as fp
+from fenapack_b200 import capi
 from fenapack_b200.petsc_shim import PC, Mat, Options, Vec
 from fenapack_b200.field_split_backend import PCDInterface
 from fenapack_b200.field_split import dofmap_dofs_is
@@ -353,3 +354,50 @@ def test_unsteady_time_loop_with_per_step_refresh():
     assert solver.krylov_iterations() / newton_its < 120
     with pytest.raises(RuntimeError):
         linear_solver.init_pcd(asm)                           # wiring happened exactly once
+
+
+@pytest.mark.gpu
+def test_krylov_operator_is_the_users_A_not_P():
+    """The Krylov MatMult must use the system matrix A in full -- including a non-zero 11 block
+    (pressure-stabilised discretisations) -- while the triangular apply cuts its blocks from P
+    (PCFIELDSPLIT, useAmat = false).  A re-assembled coupling block must reach the device."""
+    import scipy.sparse as sp
+    Options.clear()
+    m = BFSModel(level=2, variant="BRM1")
+    x0 = spla.spsolve(m._system()[0].tocsc(), m._system()[1])
+    ws = -x0
+    m.w.array[m.is_u], m.w.array[m.is_p] = ws[:m.n_u], ws[m.n_u:]          # a non-trivial wind
+    set_iterative_options("", "BRM1")
+    eps = [1e-3]
+
+    def a_stab():            # A with a (negative definite) pressure-stabilisation block
+        return (m.a() - eps[0] * m.mp()).tocsr()
+
+    def a_pc():              # P: stabilised velocity block AND a scaled 01 block
+        P = sp.lil_matrix(m.a_pc())
+        return sp.csr_matrix(P)
+    asm = fp.PCDAssembler(a_stab, m.L, [], a_pc, ap=m.ap, kp=m.kp, mp=m.mp, bcs_pcd=m.bc_pcd, function_space=m.W)
+    A, P = Mat(), Mat()
+    asm.system_matrix(A)
+    asm.pc_matrix(P)
+    ksp = fp.PCDKSP()
+    ksp.setOperators(A, P)
+    ksp.setTolerances(rtol=1e-9, max_it=500)
+    ksp.init_pcd(asm)
+    assert capi.MAT_A11 in ksp._uploaded and capi.MAT_P00 in ksp._uploaded and capi.MAT_P01 not in ksp._uploaded
+    b = Vec(np.asarray(m.L(), dtype=float))
+    x = Vec(np.zeros(m.N))
+    ksp.solve(b, x)
+    assert ksp.getConvergedReason() in (2, 3)
+    r = b.array - A.csr @ x.array
+    assert np.linalg.norm(r) <= 1e-8 * np.linalg.norm(b.array)            # A's system, 11 block included
+    # the 11 block changes (same pattern): the refresh must not keep the old one
+    eps[0] = 5e-3
+    asm.system_matrix(A)
+    ksp.solve(b, x)
+    r = b.array - A.csr @ x.array
+    assert np.linalg.norm(r) <= 1e-8 * np.linalg.norm(b.array)
+    # a convergence by the absolute tolerance is reported as such, not as a failure
+    ksp.setTolerances(rtol=1e-30, atol=1e-6 * np.linalg.norm(b.array))
+    ksp.solve(b, x)
+    assert ksp.getConvergedReason() == 3

@@ -18,16 +18,32 @@ def _ngpus():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant,p2p,repl", [("BRM1", "0", "0"), ("BRM2", "0", "0"), ("BRM1", "1", "0"),
-                                              ("BRM2", "0", "100000")])
-def test_two_rank_parity(variant, p2p, repl):
-    """p2p = "1": halo exchange through peer memory (cudaIpc) instead of NCCL send/recv;
-    repl > 0: coarse levels replicated on every rank (pc_amg_replicate_size)."""
+@pytest.mark.parametrize("variant,p2p,repl,pcdr", [("BRM1", "1", "0", "0"), ("BRM2", "1", "0", "0"), ("BRM1", "0", "0", "0"),
+                                                   ("BRM2", "0", "100000", "0"), ("BRM1", "1", "0", "1"),
+                                                   ("BRM2", "1", "0", "1")])
+def test_two_rank_parity(variant, p2p, repl, pcdr):
+    """p2p = "1" (the default): halo exchange through peer memory (cudaIpc stores, flag wait fused
+    into the consumer kernel), "0": NCCL send/recv; repl > 0: coarse levels replicated on every rank
+    (pc_amg_replicate_size); pcdr: the PCDR variants with Rp assembled across the ranks."""
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
     os.environ["FNP_P2P"] = p2p
     os.environ["FNP_REPL"] = repl
+    os.environ["FNP_PCDR"] = pcdr
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "dist_worker.py"), variant]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DIST OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["BRM1", "BRM2"])
+def test_two_rank_dropin_api(variant):
+    """PCDKrylovSolver(comm) / PCDNewtonSolver on two ranks (one GPU each): the reference's
+    mpirun path through the drop-in classes, not raw C-ABI calls."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "tests", "dist_dropin_worker.py"), variant]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DROPIN DIST OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
