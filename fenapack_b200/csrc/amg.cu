@@ -61,7 +61,7 @@ std::shared_ptr<HaloPlan> expand_plan(Ctx &c, const HaloPlan &p, int bs);
 
 static void upload_csr(Ctx &c, const HostCsr &h, DevCsr &d, const std::string &tag, int bs,
                        std::shared_ptr<HaloPlan> halo = nullptr, int64_t n_own = -1) {
-  csr_upload_pattern(c, d, h, tag, (halo && (c.overlap || c.p2p)) ? n_own : -1, bs, halo ? n_own : -1);
+  csr_upload_pattern(c, d, h, tag, (halo && c.split_rows(h.nrows)) ? n_own : -1, bs, halo ? n_own : -1);
   csr_set_values(c, d, h, h.val.data(), false);
   if (halo) {
     d.halo = bs > 1 ? expand_plan(c, *halo, bs) : halo;

@@ -18,7 +18,6 @@
 
 namespace fnp {
 
-void host_dense_inverse(const HostCsr &A, std::vector<double> &inv);
 
 static double *dev_values(DevCsr &A) { return A.sell ? A.sl_val.p : A.val.p; }
 static int64_t dev_nvalues(const DevCsr &A) { return A.sell ? A.sell_entries : A.nnz; }
@@ -45,7 +44,9 @@ static void build_plans(Ctx &c, DevHierarchy &H) {
     const HostLevel &hf = H.host.levels[l], &hc = H.host.levels[l + 1];
     GalerkinPlan plan;
     try {
-      build_galerkin_plan(hf.A, hf.P, hf.R, hc.A, plan);
+      // several ranks: P with the rows of the ghost dofs, columns in the coarse level's local numbering
+      // (amg_setup.cpp); the plan then involves this rank's values only -- no communication at refresh
+      build_galerkin_plan(hf.A, hf.Pext.nrows > 0 ? hf.Pext : hf.P, hf.R, hc.A, plan);
     } catch (const std::exception &e) {
       throw Error(FNP_ERR_STATE, e.what());
     }
@@ -112,7 +113,7 @@ static void build_plans(Ctx &c, DevHierarchy &H) {
 
 void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs) {
   FNP_REQUIRE(H.built && !H.levels.empty(), FNP_ERR_STATE, "AMG hierarchy not built");
-  FNP_REQUIRE(c.nranks == 1 && !H.tail, FNP_ERR_OPTION, "pc_amg_refresh galerkin is available on single-rank contexts only");
+  FNP_REQUIRE(!H.tail, FNP_ERR_OPTION, "pc_amg_refresh galerkin does not cover a replicated coarse tail (pc_amg_replicate_size)");
   FNP_REQUIRE(H.params.coarse_drop == 0.0, FNP_ERR_OPTION, "pc_amg_refresh galerkin needs pc_amg_coarse_drop 0");
   const size_t L = H.levels.size();
   StageTimer t(c, "FENaPack: AMG Galerkin refresh");
@@ -138,10 +139,8 @@ void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs) {
     for (int64_t k = 0; k < h.nnz(); ++k) h.val[(size_t)k] = buf[(size_t)dev_position(A, k)];
   }
   if (L > 1) {
-    const HostCsr &hc = H.host.levels.back().A;
-    host_dense_inverse(hc, H.host.coarse_inv);
-    const int64_t nc = hc.nrows, cols = H.host.coarse_cols;
-    FNP_REQUIRE(cols == nc, FNP_ERR_STATE, "unexpected coarse inverse shape");
+    // collective on several ranks: the coarsest rows are gathered and inverted redundantly
+    amg_coarse_inverse_host(c, H.host);
     H.coarse_inv.upload(H.host.coarse_inv.data(), H.host.coarse_inv.size(), c.stream);
     FNP_CUDA(cudaStreamSynchronize(c.stream));
   }

@@ -553,6 +553,36 @@ void amg_build_host(Ctx &c, const HostCsr &A0, std::vector<int64_t> begins, cons
       dg = halo_exchange_host(c, *cplan, down);
     }
     filter_lumped(Aloc, p.coarse_drop, dg, &gcol);
+    if (R > 1) {
+      // frozen-P Galerkin refresh (amg_refresh.cu) on several ranks: keep P with the ghost rows, columns
+      // translated from the compact numbering [my aggregates | foreign] to the next level's local
+      // numbering [owned | ghost]; foreign columns that never meet a local row are dropped
+      HostLevel &cur = H.levels.back();
+      cur.Pext = Pext;
+      HostCsr &Q = cur.Pext;
+      Q.ncols = nagg + (int64_t)cghosts.size();
+      std::vector<int32_t> rp(Q.nrows + 1, 0);
+      int64_t o = 0;
+      for (int64_t i = 0; i < Q.nrows; ++i) {
+        for (int32_t k = Pext.rowptr[i]; k < Pext.rowptr[i + 1]; ++k) {
+          const int32_t l = Pext.col[k];
+          int32_t loc = l;
+          if (l >= nagg) {
+            const int64_t g = foreign[l - nagg];
+            const auto it = std::lower_bound(cghosts.begin(), cghosts.end(), g);
+            loc = (it != cghosts.end() && *it == g) ? (int32_t)(nagg + (it - cghosts.begin())) : -1;
+          }
+          if (loc < 0) continue;
+          Q.col[o] = loc;
+          Q.val[o] = Pext.val[k];
+          ++o;
+        }
+        rp[i + 1] = (int32_t)o;
+      }
+      Q.rowptr.swap(rp);
+      Q.col.resize(o);
+      Q.val.resize(o);
+    }
     Ag = std::move(Aloc);
     Ag.col = std::move(gcol);
     Ag.ncols = cbegins[R];
@@ -603,39 +633,46 @@ void amg_build_host(Ctx &c, const HostCsr &A0, std::vector<int64_t> begins, cons
   }
   // coarsest level: every rank inverts the (small) global matrix and keeps its own rows,
   // columns laid out as the padded all-gather of the right-hand side delivers them
-  {
-    HostLevel &lvl = H.levels.back();
-    const int64_t n = lvl.n_own, ng = begins[R];
-    int64_t maxloc = 0;
-    for (int q = 0; q < R; ++q) maxloc = std::max(maxloc, begins[q + 1] - begins[q]);
-    FNP_REQUIRE(ng <= 8192, FNP_ERR_NUMERIC, "AMG coarsening stalled: coarsest level has " + std::to_string(ng) + " rows");
-    std::vector<double> rows((size_t)n * ng, 0.0);
-    for (int64_t i = 0; i < n; ++i)
-      for (int32_t k = Ag.rowptr[i]; k < Ag.rowptr[i + 1]; ++k) rows[(size_t)i * ng + Ag.col[k]] = Ag.val[k];
-    std::vector<double> all = comm_allgather_padded(c, rows.data(), n * ng, maxloc * ng);
-    HostCsr dense;      // reuse dense_inverse through a CSR view of the dense matrix
-    dense.nrows = dense.ncols = ng;
-    dense.rowptr.resize(ng + 1);
-    dense.col.resize((size_t)ng * ng);
-    dense.val.resize((size_t)ng * ng);
-    for (int64_t gi = 0; gi <= ng; ++gi) dense.rowptr[gi] = (int32_t)(gi * ng);
+  H.coarse_gcol = Ag.col;
+  H.coarse_begins = begins;
+  amg_coarse_inverse_host(c, H);
+}
+
+void amg_coarse_inverse_host(Ctx &c, HostHierarchy &H) {
+  const int me = c.rank, R = c.nranks;
+  const std::vector<int64_t> &begins = H.coarse_begins;
+  HostLevel &lvl = H.levels.back();
+  const HostCsr &A = lvl.A;              // values current; global columns in H.coarse_gcol
+  const int64_t n = lvl.n_own, ng = begins[R];
+  int64_t maxloc = 0;
+  for (int q = 0; q < R; ++q) maxloc = std::max(maxloc, begins[q + 1] - begins[q]);
+  FNP_REQUIRE(ng <= 8192, FNP_ERR_NUMERIC, "AMG coarsening stalled: coarsest level has " + std::to_string(ng) + " rows");
+  std::vector<double> rows((size_t)n * ng, 0.0);
+  for (int64_t i = 0; i < n; ++i)
+    for (int32_t k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) rows[(size_t)i * ng + H.coarse_gcol[k]] = A.val[k];
+  std::vector<double> all = comm_allgather_padded(c, rows.data(), n * ng, maxloc * ng);
+  HostCsr dense;      // reuse dense_inverse through a CSR view of the dense matrix
+  dense.nrows = dense.ncols = ng;
+  dense.rowptr.resize(ng + 1);
+  dense.col.resize((size_t)ng * ng);
+  dense.val.resize((size_t)ng * ng);
+  for (int64_t gi = 0; gi <= ng; ++gi) dense.rowptr[gi] = (int32_t)(gi * ng);
+  for (int q = 0; q < R; ++q)
+    for (int64_t i = 0; i < begins[q + 1] - begins[q]; ++i)
+      for (int64_t j = 0; j < ng; ++j) {
+        const int64_t gi = begins[q] + i;
+        dense.col[(size_t)gi * ng + j] = (int32_t)j;
+        dense.val[(size_t)gi * ng + j] = all[(size_t)q * maxloc * ng + (size_t)i * ng + j];
+      }
+  std::vector<double> inv;
+  dense_inverse(dense, inv);
+  H.coarse_cols = R * maxloc;
+  H.coarse_maxloc = maxloc;
+  H.coarse_inv.assign((size_t)n * H.coarse_cols, 0.0);
+  for (int64_t i = 0; i < n; ++i)
     for (int q = 0; q < R; ++q)
-      for (int64_t i = 0; i < begins[q + 1] - begins[q]; ++i)
-        for (int64_t j = 0; j < ng; ++j) {
-          const int64_t gi = begins[q] + i;
-          dense.col[(size_t)gi * ng + j] = (int32_t)j;
-          dense.val[(size_t)gi * ng + j] = all[(size_t)q * maxloc * ng + (size_t)i * ng + j];
-        }
-    std::vector<double> inv;
-    dense_inverse(dense, inv);
-    H.coarse_cols = R * maxloc;
-    H.coarse_maxloc = maxloc;
-    H.coarse_inv.assign((size_t)n * H.coarse_cols, 0.0);
-    for (int64_t i = 0; i < n; ++i)
-      for (int q = 0; q < R; ++q)
-        for (int64_t t = 0; t < begins[q + 1] - begins[q]; ++t)
-          H.coarse_inv[(size_t)i * H.coarse_cols + q * maxloc + t] = inv[(size_t)(begins[me] + i) * ng + begins[q] + t];
-  }
+      for (int64_t t = 0; t < begins[q + 1] - begins[q]; ++t)
+        H.coarse_inv[(size_t)i * H.coarse_cols + q * maxloc + t] = inv[(size_t)(begins[me] + i) * ng + begins[q] + t];
 }
 
 }  // namespace fnp

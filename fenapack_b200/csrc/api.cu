@@ -226,6 +226,8 @@ static void set_option(Ctx &c, const std::string &name, const std::string &v) {
     c.refresh_chunk_terms = std::max<int64_t>(1, (int64_t)parse_real(name, v));
   } else if (name == "fnp_sell_warps_rows") {
     c.sell_warps_rows = (int64_t)parse_real(name, v);
+  } else if (name == "fnp_halo_split_rows") {
+    c.halo_split_rows = (int64_t)parse_real(name, v);
   } else if (name == "fnp_gmres_sync") {
     c.gmres_sync = parse_int(name, v);
   } else if (name == "fnp_sell_warps") {

@@ -279,6 +279,8 @@ struct AmgParams {
 
 struct HostLevel {
   HostCsr A, P, R;                  // A: local rows, columns [owned | ghost]; P, R: rank local
+  HostCsr Pext;                     // multi-rank: P with the rows of A's ghost dofs appended and the columns in the
+                                    // local numbering [owned | ghost] of the next level (frozen-P Galerkin refresh)
   std::vector<double> dinv;
   double rho = 1.0;
   std::shared_ptr<HaloPlan> halo;   // null on single-rank contexts
@@ -290,6 +292,8 @@ struct HostHierarchy {
   std::vector<HostLevel> levels;
   std::vector<double> coarse_inv;   // dense row-major [n_own x coarse_cols]
   int64_t coarse_cols = 0, coarse_maxloc = 0;
+  std::vector<int32_t> coarse_gcol; // global column id of every stored entry of the coarsest level
+  std::vector<int64_t> coarse_begins;   // ownership offsets of the coarsest level
   // multi-rank: from the first level with <= replicate_size global rows on, the hierarchy is
   // built and applied redundantly on every rank (one all-gather per V-cycle instead of a halo
   // exchange per SpMV on levels whose kernels are far shorter than an exchange)
@@ -299,6 +303,8 @@ struct HostHierarchy {
 
 void host_spgemm(const HostCsr &A, const HostCsr &B, HostCsr &C);     // C = A B, rows sorted
 void host_transpose(const HostCsr &A, HostCsr &T);
+// dense inverse of the coarsest level from its current values (collective: the rows are gathered)
+void amg_coarse_inverse_host(Ctx &c, HostHierarchy &H);
 void amg_build_host(Ctx &c, const HostCsr &A_global_cols, std::vector<int64_t> begins, const AmgParams &p,
                     HostHierarchy &H, int level0 = 0);
 
@@ -464,7 +470,12 @@ struct Ctx {
 
   // CUDA graph of one block-triangular PC apply on fixed staging buffers (single-rank
   // contexts): ~500 short launches per apply collapse into one graph launch
-  int p2p = 1;                  // 1: peer-memory halo exchange (cudaIpc stores + flags, wait fused into the consumer
+  int64_t halo_split_rows = 50000;   // operators with at least this many rows are split into interior / boundary rows
+                                     // (interior rows overlap the exchange); smaller ones wait in one kernel
+  bool split_rows(int64_t nrows) const { return overlap || (p2p && nrows >= halo_split_rows); }
+  int p2p = 1;                  // 2: as 1, and the pack + remote-store kernel of a split operator runs on a forked stream
+                                // beside the interior rows;
+                                // 1: peer-memory halo exchange (cudaIpc stores + flags, wait fused into the consumer
                                 // kernel, device-resident sequence numbers); 0: NCCL send/recv
   DevBuf<int> p2p_err;          // set by a timed-out flag wait
   int overlap = 0;              // 1: split SELL operators into interior/boundary rows and overlap the halo exchange

@@ -211,7 +211,7 @@ static void finalize_pattern(Ctx &c, int which, const int32_t *rowptr, const int
     HostCsr loc = h;
     std::shared_ptr<HaloPlan> plan = build_halo(c, loc, begins, nullptr);
     const int64_t n_own_cols = begins[c.rank + 1] - begins[c.rank];
-    csr_upload_pattern(c, d, loc, kNames[which], (c.overlap || c.p2p) ? n_own_cols : -1, bs, n_own_cols);
+    csr_upload_pattern(c, d, loc, kNames[which], c.split_rows(loc.nrows) ? n_own_cols : -1, bs, n_own_cols);
     d.halo = (plan && bs > 1) ? expand_plan(c, *plan, bs) : plan;
     d.ncols_own = (int32_t)n_own_cols;
     d.nghost = plan ? plan->nghost : 0;

@@ -660,9 +660,19 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
   const double *xg = nullptr;
   int nown = INT32_MAX;
   const int threads = 256;
+  // peer-memory exchange of a split operator, option fnp_halo_p2p 2: the pack + remote-store kernel runs
+  // on a forked stream beside the interior rows (fork / join by events: capturable)
+  const bool fork_send = A.halo && A.halo->p2p && c.p2p >= 2 && A.sell && A.nslices_b > 0 && c.comm_stream && c.ev_x;
   if (A.halo) {
     // post the exchange of the ghost entries of x (peer-memory stores or NCCL send/recv)
-    halo_exchange(c, *A.halo, x, c.stream, c.comm);
+    if (fork_send) {
+      FNP_CUDA(cudaEventRecord(c.ev_x, c.stream));
+      FNP_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_x, 0));
+      halo_exchange(c, *A.halo, x, c.comm_stream, c.comm);
+      FNP_CUDA(cudaEventRecord(c.ev_halo, c.comm_stream));
+    } else {
+      halo_exchange(c, *A.halo, x, c.stream, c.comm);
+    }
     xg = A.halo->current_ghost;
     nown = A.ncols_own;
   }
@@ -714,6 +724,7 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
       // split operator: the interior rows (no ghost column) run while the ghost entries are in
       // flight; the boundary rows wait for the flags inside their kernel
       launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0, nullptr);
+      if (fork_send) FNP_CUDA(cudaStreamWaitEvent(c.stream, c.ev_halo, 0));     // join: x may be overwritten afterwards
       launch(A.nslices_b, A.sl_ptr_b.p, A.sl_perm_b.p, A.sell_entries_a, hw_ghost);
     } else {
       launch(A.nslices, A.sl_ptr.p, A.sl_perm.p, 0, hw_ghost);

@@ -332,7 +332,7 @@ static void build_rp(Ctx &c) {
   HostCsr loc = R;
   std::shared_ptr<HaloPlan> plan = build_halo(c, loc, c.p_begins, nullptr);
   const int64_t n_own = c.n_p;
-  csr_upload_pattern(c, c.rp, loc, "Rp", (plan && (c.overlap || c.p2p)) ? n_own : -1, 1, plan ? n_own : -1);
+  csr_upload_pattern(c, c.rp, loc, "Rp", (plan && c.split_rows(loc.nrows)) ? n_own : -1, 1, plan ? n_own : -1);
   c.rp.halo = plan;
   if (plan) {
     c.rp.ncols_own = (int32_t)n_own;
@@ -382,7 +382,7 @@ void setup_all(Ctx &c) {
     // A pattern rebuild of the block (pruning found a new non-zero) invalidates the hierarchy.
     const bool same_shape = c.amg_u.built && !c.amg_u.levels.empty() && c.amg_u.levels[0].Ap == &c.dmat[uidx] &&
                             c.amg_u_gen == c.pattern_gen[uidx] && c.amg_u_which == uidx;
-    if (same_shape && c.opt_u.amg.refresh == 1 && c.nranks == 1 && c.opt_u.amg.coarse_drop == 0.0) {
+    if (same_shape && c.opt_u.amg.refresh == 1 && !c.amg_u.tail && c.opt_u.amg.coarse_drop == 0.0) {
       amg_refresh_device(c, c.amg_u, c.kron_bs[uidx]);
     } else if (same_shape && c.amg_u_age + 1 < c.opt_u.amg.lag) {
       ++c.amg_u_age;

@@ -122,14 +122,38 @@ def parity_check(rank, world, local, variant="BRM1", extra_options=None, p2p=Non
     xs = np.concatenate([x_ref[:prob.n_u][u0:u1], x_ref[prob.n_u:][p0:p1]])
     out["solution_relerr"] = relerr(np.concatenate([su, sp_]), xs)
     assert out["solution_relerr"] <= 1e-5
+    keys = ["spmv_relerr", "ap_solve_relerr", "u_solve_relerr", "pc_apply_relerr", "solution_relerr"]
+    if not pcdr and not repl:
+        # value refresh on several ranks: new velocity-block values (same pattern, Kronecker structure kept),
+        # coarse operators recomputed on the device with frozen prolongators -- rank local, no communication
+        import scipy.sparse as sp
+        which = capi.MAT_P00 if prob.P00 is not None else capi.MAT_A00
+        A2 = sp.csr_matrix(P00, copy=True)
+        d = A2.diagonal()
+        A2.setdiag(d * (1.0 + 0.3 * np.repeat(np.sin(np.arange(prob.n_u // dim)), dim) ** 2))
+        A2.sort_indices()
+        assert np.array_equal(A2.indices, P00.indices)
+        ctx.set_values(which, A2[u0:u1, :].tocsr().data)
+        ctx.setup()
+        Hr = oamg.Hierarchy(smooth_steps=Hu.smooth_steps, eig_ratio=Hu.eig_ratio)
+        Ak = A2
+        for k, old in enumerate(Hu.levels):
+            dk = Ak.diagonal()
+            Hr.levels.append(oamg.Level(A=Ak, dinv=np.where(dk != 0, 1.0 / np.where(dk != 0, dk, 1.0), 0.0), rho=old.rho,
+                                        P=old.P, R=old.R))
+            if k + 1 < len(Hu.levels):
+                Ak = (old.R @ Ak @ old.P).tocsr()
+        Hr.coarse_inv = np.linalg.inv(Hr.levels[-1].A.toarray())
+        out["refresh_u_solve_relerr"] = relerr(ctx.u_solve(bu[u0:u1]), Hr(bu)[u0:u1])
+        assert out["refresh_u_solve_relerr"] <= 1e-9, ("refresh", out["refresh_u_solve_relerr"])
+        keys.append("refresh_u_solve_relerr")
     out.update({"its": int(its), "oracle_its": int(its_ref), "ndofs": int(prob.n_u + prob.n_p),
                 "problem": ("unsteady BFS level 3 PCDR " + variant) if pcdr else
                            ("channel 12x4x6 BRM1" if variant == "BRM1" else "cavity 8^3 BRM2")})
     # worst case over the ranks (each rank checked its own rows)
-    t = torch.tensor([out[k] for k in ("spmv_relerr", "ap_solve_relerr", "u_solve_relerr", "pc_apply_relerr",
-                                       "solution_relerr")], dtype=torch.float64, device="cuda")
+    t = torch.tensor([out[k] for k in keys], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    for k, v in zip(("spmv_relerr", "ap_solve_relerr", "u_solve_relerr", "pc_apply_relerr", "solution_relerr"), t.tolist()):
+    for k, v in zip(keys, t.tolist()):
         out[k] = v
     ctx.close()
     return out

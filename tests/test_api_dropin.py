@@ -370,8 +370,9 @@ def test_krylov_operator_is_the_users_A_not_P():
     set_iterative_options("", "BRM1")
     eps = [1e-3]
 
-    def a_stab():            # A with a (negative definite) pressure-stabilisation block
-        return (m.a() - eps[0] * m.mp()).tocsr()
+    def a_stab():            # A with a (negative definite) pressure-stabilisation block; stored pattern kept
+        from fem_forms import struct_add
+        return struct_add(m.a(), -eps[0] * m.mp())
 
     def a_pc():              # P: stabilised velocity block AND a scaled 01 block
         P = sp.lil_matrix(m.a_pc())
