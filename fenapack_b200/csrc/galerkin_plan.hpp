@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <stdexcept>
+#include <utility>
 #include <vector>
 
 namespace fnp {
@@ -29,10 +30,36 @@ void build_galerkin_plan(const Csr &A, const Csr &P, const Csr &R, const Csr &Ac
   const int64_t nc = (int64_t)Ac.rowptr.size() - 1;
   const int64_t nq = Ac.rowptr.empty() ? 0 : Ac.rowptr.back();
   W.ptr.assign(nq + 1, 0);
+  // column-sorted view of every coarse row (on several ranks the rows of Ac are in the local numbering
+  // [owned | ghost], which is not ascending along a row): scol = columns sorted, sq = entry index
+  std::vector<int32_t> scol(Ac.col.begin(), Ac.col.begin() + nq);
+  std::vector<int64_t> sq((size_t)nq);
+#pragma omp parallel
+  {
+    std::vector<std::pair<int32_t, int64_t>> row;
+#pragma omp for schedule(static)
+    for (int64_t I = 0; I < nc; ++I) {
+      const int64_t b = Ac.rowptr[I], e = Ac.rowptr[I + 1];
+      bool sorted = true;
+      for (int64_t k = b + 1; k < e; ++k)
+        if (Ac.col[k - 1] > Ac.col[k]) { sorted = false; break; }
+      if (sorted) {
+        for (int64_t k = b; k < e; ++k) sq[(size_t)k] = k;
+        continue;
+      }
+      row.clear();
+      for (int64_t k = b; k < e; ++k) row.push_back({Ac.col[k], k});
+      std::sort(row.begin(), row.end());
+      for (int64_t k = b; k < e; ++k) {
+        scol[(size_t)k] = row[(size_t)(k - b)].first;
+        sq[(size_t)k] = row[(size_t)(k - b)].second;
+      }
+    }
+  }
   auto find = [&](int64_t I, int32_t J) -> int64_t {
-    const int32_t *b = Ac.col.data() + Ac.rowptr[I], *e = Ac.col.data() + Ac.rowptr[I + 1];
+    const int32_t *b = scol.data() + Ac.rowptr[I], *e = scol.data() + Ac.rowptr[I + 1];
     const int32_t *it = std::lower_bound(b, e, J);
-    return (it != e && *it == J) ? (int64_t)(it - Ac.col.data()) : -1;
+    return (it != e && *it == J) ? sq[(size_t)(it - scol.data())] : -1;
   };
   bool missing = false;
   // pass 1: terms per coarse entry (row I owns the entries [Ac.rowptr[I], Ac.rowptr[I+1]))

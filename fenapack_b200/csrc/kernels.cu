@@ -947,7 +947,9 @@ void dot(Ctx &c, int64_t n, const double *x, const double *y, double *out_dev) {
   FNP_LAUNCH_CHECK(c);
 }
 
-// w -= sum_i h[i] V_i, partial = block sums of w_new^2
+// w -= sum_i h[i] V_i, partial = block sums of w_new^2.  Two consecutive elements per thread with
+// 16-byte loads, four basis vectors in flight: 128 bytes of loads outstanding per thread (round 2:
+// the 8-byte version reached 0.59 of the HBM peak at 53 M dofs -- too few bytes in flight).
 __global__ void __launch_bounds__(RED_THREADS)
 maxpy_norm_kernel(int64_t n, const double *const *__restrict__ V, int nvec, const double *__restrict__ h,
                   double *__restrict__ w, double *__restrict__ partial) {
@@ -955,17 +957,33 @@ maxpy_norm_kernel(int64_t n, const double *const *__restrict__ V, int nvec, cons
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) sh[i] = h[i];
   __syncthreads();
   double acc = 0.0;
-  GRID_STRIDE(e, n) {
-    double wv = w[e];
+  const int64_t n2 = n >> 1;
+  double2 *w2 = reinterpret_cast<double2 *>(w);
+  GRID_STRIDE(e, n2) {
+    double2 wv = w2[e];
     int i = 0;
     for (; i + 4 <= nvec; i += 4) {
-      const double a0 = __ldg(V[i] + e), a1 = __ldg(V[i + 1] + e), a2 = __ldg(V[i + 2] + e), a3 = __ldg(V[i + 3] + e);
-      wv -= sh[i] * a0;
-      wv -= sh[i + 1] * a1;
-      wv -= sh[i + 2] * a2;
-      wv -= sh[i + 3] * a3;
+      const double2 a0 = __ldg(reinterpret_cast<const double2 *>(V[i]) + e);
+      const double2 a1 = __ldg(reinterpret_cast<const double2 *>(V[i + 1]) + e);
+      const double2 a2 = __ldg(reinterpret_cast<const double2 *>(V[i + 2]) + e);
+      const double2 a3 = __ldg(reinterpret_cast<const double2 *>(V[i + 3]) + e);
+      wv.x -= sh[i] * a0.x;     wv.y -= sh[i] * a0.y;
+      wv.x -= sh[i + 1] * a1.x; wv.y -= sh[i + 1] * a1.y;
+      wv.x -= sh[i + 2] * a2.x; wv.y -= sh[i + 2] * a2.y;
+      wv.x -= sh[i + 3] * a3.x; wv.y -= sh[i + 3] * a3.y;
     }
-    for (; i < nvec; ++i) wv -= sh[i] * __ldg(V[i] + e);
+    for (; i < nvec; ++i) {
+      const double2 a0 = __ldg(reinterpret_cast<const double2 *>(V[i]) + e);
+      wv.x -= sh[i] * a0.x;
+      wv.y -= sh[i] * a0.y;
+    }
+    w2[e] = wv;
+    acc += wv.x * wv.x + wv.y * wv.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {      // odd length: the last element
+    const int64_t e = n - 1;
+    double wv = w[e];
+    for (int i = 0; i < nvec; ++i) wv -= sh[i] * __ldg(V[i] + e);
     w[e] = wv;
     acc += wv * wv;
   }

@@ -32,7 +32,7 @@ def test_two_rank_parity(variant, p2p, repl, pcdr):
     os.environ["FNP_PCDR"] = pcdr
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "dist_worker.py"), variant]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "DIST OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
@@ -45,5 +45,5 @@ def test_two_rank_dropin_api(variant):
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "tests", "dist_dropin_worker.py"), variant]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "DROPIN DIST OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -226,6 +226,30 @@ def test_spmv_kernel_variants(kernel):
     ctx.close()
 
 
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+@pytest.mark.parametrize("kron", [1, 0])
+def test_multi_warp_sell_kernel(warps, kron):
+    """spmv_sell_mw_kernel: T warps share a SELL slice (the kernel chosen for operators with few
+    rows, e.g. AMG levels >= 1).  Forced for every operator here, with and without the Kronecker
+    mode of the velocity block: products, the fused Chebyshev sweep and the whole apply."""
+    prob, _ = problems.channel(12, 4, 4, variant="BRM1")
+    ctx = make_context(prob, {"fnp_spmv_kernel": "sell", "fnp_sell_warps": warps, "fnp_kronecker": kron})
+    rng = np.random.default_rng(12)
+    for which, A in ((capi.MAT_A00, prob.A00), (capi.MAT_A01, prob.A01), (capi.MAT_A10, prob.A10),
+                     (capi.MAT_AP, prob.Ap), (capi.MAT_KP, prob.Kp)):
+        x = rng.standard_normal(A.shape[1])
+        assert relerr(ctx.spmv(which, x, A.shape[0]), A @ x) <= TOL_SPMV
+    b = rng.standard_normal(prob.n_p)
+    dinv = 1.0 / prob.Mp.diagonal()
+    assert relerr(ctx.mp_solve(b), pa.chebyshev_jacobi(prob.Mp, dinv, b, *prob.cheb_bounds, 5)) <= TOL_SPMV
+    pc = oracle_preconditioner(prob, ctx)
+    xu, xp = rng.standard_normal(prob.n_u), rng.standard_normal(prob.n_p)
+    yu, yp = ctx.pc_apply(xu, xp)
+    ru, rp = pc.apply_split(xu, xp)
+    assert relerr(yp, rp) <= TOL_PC and relerr(yu, ru) <= TOL_PC
+    ctx.close()
+
+
 def test_kronecker_detection_and_general_path_agree():
     """The Picard velocity block is recognised as S (x) I_d (stored and coarsened as S);
     with the detection switched off the general path must give the same preconditioner

@@ -65,6 +65,24 @@ def test_galerkin_plan_cxx_matches_oracle(harness):
         ref = np.array([G[i, j] for i, j in zip(np.repeat(np.arange(nc), np.diff(Ac.indptr)), Ac.indices)])
         assert np.allclose(got, ref, rtol=0, atol=1e-13 * max(1.0, abs(ref).max()))
         assert np.allclose(got, W_ref @ vals, rtol=0, atol=1e-13 * max(1.0, abs(ref).max()))
+    # coarse rows that are not sorted by column (several ranks: local numbering [owned | ghost]): same plan,
+    # rows of W follow the entry order given
+    lvl = H.levels[0]
+    A, a = _args(lvl.A)
+    P, p = _args(lvl.P)
+    R, r = _args(lvl.P.T)
+    pat, W_ref = amg.galerkin_plan(A, P)
+    rp = pat.indptr.astype(np.int32)
+    perm = np.concatenate([np.arange(rp[i + 1] - 1, rp[i] - 1, -1) for i in range(pat.shape[0])])     # every row reversed
+    ci_rev = np.ascontiguousarray(pat.indices[perm].astype(np.int32))
+    va = np.ones(pat.nnz)
+    terms = harness.plan_build(C.c_int64(A.shape[0]), C.c_int64(P.shape[1]), *[_ptr(v) for v in a + p + r + (rp, ci_rev, va)])
+    assert terms == W_ref.nnz
+    ptr, src, coef = np.empty(pat.nnz + 1, dtype=np.int64), np.empty(terms, dtype=np.int32), np.empty(terms)
+    harness.plan_copy(_ptr(ptr), _ptr(src), _ptr(coef))
+    W = sp.csr_matrix((coef, src, ptr), shape=(pat.nnz, A.nnz))
+    vals = np.random.default_rng(5).standard_normal(A.nnz)
+    assert np.allclose(W @ vals, (W_ref @ vals)[perm], rtol=0, atol=1e-13 * abs(W_ref @ vals).max())
     # a coarse pattern that misses product entries is reported, not silently accepted
     A, a = _args(H.levels[0].A)
     P, p = _args(H.levels[0].P)
