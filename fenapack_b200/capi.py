@@ -60,6 +60,8 @@ SIGNATURES = {
     "fnp_get_converged_reason": (C.c_int, [C.c_void_p, _c_int32_p]),
     "fnp_get_residual_history": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "fnp_operator_block_size": (C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
+    "fnp_rp_info": (C.c_int, [C.c_void_p, _c_int64_p, _c_int64_p]),
+    "fnp_rp_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fnp_amg_num_levels": (C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
     "fnp_amg_level_info": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_int64_p, _c_int64_p,
                                      _c_int64_p, _c_double_p]),
@@ -333,6 +335,17 @@ class Context:
         cinv = np.empty((nc, nc))
         _check(self._lib.fnp_amg_coarse_inverse(self._h, which, _ptr(cinv)))
         return levels, cinv
+
+    def rp_local_rows(self, n_p_global):
+        """This rank's rows of the derived PCDR operator Rp (scipy CSR, global column ids)."""
+        import scipy.sparse as sp
+        nr, nnz = C.c_int64(), C.c_int64()
+        _check(self._lib.fnp_rp_info(self._h, C.byref(nr), C.byref(nnz)))
+        rp = np.empty(nr.value + 1, dtype=np.int32)
+        ci = np.empty(nnz.value, dtype=np.int32)
+        va = np.empty(nnz.value)
+        _check(self._lib.fnp_rp_get(self._h, _ptr(rp), _ptr(ci), _ptr(va)))
+        return sp.csr_matrix((va, ci, rp), shape=(nr.value, n_p_global))
 
     def block_size(self, which):
         bs = C.c_int32()

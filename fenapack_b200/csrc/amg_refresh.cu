@@ -19,6 +19,8 @@
 namespace fnp {
 
 
+double comm_allreduce(Ctx &c, double v, bool max_op);
+
 static double *dev_values(DevCsr &A) { return A.sell ? A.sl_val.p : A.val.p; }
 static int64_t dev_nvalues(const DevCsr &A) { return A.sell ? A.sell_entries : A.nnz; }
 static int64_t dev_position(const DevCsr &A, int64_t k) { return A.sell ? (int64_t)A.sell_pos[(size_t)k] : k; }
@@ -117,7 +119,24 @@ void amg_refresh_device(Ctx &c, DevHierarchy &H, int bs) {
   FNP_REQUIRE(H.params.coarse_drop == 0.0, FNP_ERR_OPTION, "pc_amg_refresh galerkin needs pc_amg_coarse_drop 0");
   const size_t L = H.levels.size();
   StageTimer t(c, "FENaPack: AMG Galerkin refresh");
-  if (L > 1 && !H.refresh_built) build_plans(c, H);
+  if (L > 1 && !H.refresh_built) {
+    // host work without collectives: a failure on one rank must not leave the others waiting in the
+    // gather of the coarsest level below
+    std::string err;
+    try {
+      build_plans(c, H);
+    } catch (const std::exception &e) {
+      err = e.what();
+    }
+    const double failed = comm_allreduce(c, err.empty() ? 0.0 : 1.0, true);
+    if (failed > 0.5) {
+      H.refresh_W.clear();
+      H.refresh_row0.clear();
+      H.refresh_diag.clear();
+      H.refresh_built = false;
+      throw Error(FNP_ERR_STATE, err.empty() ? std::string("Galerkin refresh plan failed on another rank") : err);
+    }
+  }
   for (size_t l = 0; l + 1 < L; ++l) {
     DevCsr &Af = H.levels[l].A(), &Ac = H.levels[l + 1].A();
     for (size_t ch = 0; ch < H.refresh_W[l].size(); ++ch)

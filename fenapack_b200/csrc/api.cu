@@ -645,6 +645,26 @@ int fnp_solve_monolithic(fnp_context *ctx, const double *b, double *x, int on_de
   FNP_API_END
 }
 
+int fnp_rp_info(fnp_context *ctx, int64_t *nrows_local, int64_t *nnz) {
+  FNP_API_BEGIN
+  CTX(ctx);
+  FNP_REQUIRE(c.variant >= 3 && c.h_rp.nrows > 0, FNP_ERR_STATE, "Rp exists for the PCDR variants after fnp_setup only");
+  if (nrows_local) *nrows_local = c.h_rp.nrows;
+  if (nnz) *nnz = c.h_rp.nnz();
+  FNP_API_END
+}
+
+int fnp_rp_get(fnp_context *ctx, int32_t *rowptr, int32_t *colidx_global, double *values) {
+  FNP_API_BEGIN
+  CTX(ctx);
+  FNP_REQUIRE(c.variant >= 3 && c.h_rp.nrows > 0, FNP_ERR_STATE, "Rp exists for the PCDR variants after fnp_setup only");
+  FNP_REQUIRE(rowptr && colidx_global && values, FNP_ERR_ARG, "null output");
+  std::memcpy(rowptr, c.h_rp.rowptr.data(), c.h_rp.rowptr.size() * sizeof(int32_t));
+  std::memcpy(colidx_global, c.h_rp.col.data(), c.h_rp.col.size() * sizeof(int32_t));
+  std::memcpy(values, c.h_rp.val.data(), c.h_rp.val.size() * sizeof(double));
+  FNP_API_END
+}
+
 int fnp_get_converged_reason(fnp_context *ctx, int32_t *reason) {
   if (!ctx || !reason) return FNP_ERR_ARG;
   *reason = ctx->c.converged_reason;

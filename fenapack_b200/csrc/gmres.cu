@@ -53,8 +53,6 @@ struct Basis {
 
 constexpr double ST_OK = 0.0, ST_NONFINITE = 1.0, ST_CANCELLATION = 2.0;
 
-struct Cancellation {};
-
 }  // namespace
 
 // Device-side state of one restart cycle: H (m+1) x m column major, cs, sn, g, and per iteration
@@ -165,7 +163,6 @@ static void solve_impl(Ctx &c, const double *b, double *x, int32_t *its_out, dou
   double *hdev = c.red_out.p;          // [0, j]: h column, [j+1]: w.w   ([1000..]: CG scalars, pcd.cu)
   double *nrm_loc = c.red_out.p + 996; // explicit ||w||^2 after the orthogonalisation
   double *hpin = c.pinned;
-  const bool pythagoras = c.nranks > 1 && !c.gmres_two_reductions;
 
   // ||b||
   dot(c, n, b, b, hdev);
@@ -198,11 +195,18 @@ static void solve_impl(Ctx &c, const double *b, double *x, int32_t *its_out, dou
     int enq = 0;                   // iterations enqueued in this cycle
     int seen = 0;                  // iterations whose result the host has looked at
     double prev_res = beta, last_res = beta;
+    bool cancelled = false;
     // look at the result of iteration `seen` (waits for its event); true when the cycle ends there
     auto consume = [&]() -> bool {
       FNP_CUDA(cudaEventSynchronize(c.ev_iter[seen & 1]));
       const double r = hpin[2 + 2 * seen], st = hpin[2 + 2 * seen + 1];
-      if (st == ST_CANCELLATION) throw Cancellation();
+      if (st == ST_CANCELLATION) {
+        // the norm from the single reduction lost its digits: close the cycle before this column, update
+        // x, restart from the true residual with the explicit norm (every rank sees the same numbers)
+        cancelled = true;
+        jdone = seen;
+        return true;
+      }
       FNP_REQUIRE(st == ST_OK && std::isfinite(r), FNP_ERR_NUMERIC, "GMRES breakdown: non-finite Hessenberg entry");
       prev_res = last_res;
       last_res = r;
@@ -232,6 +236,11 @@ static void solve_impl(Ctx &c, const double *b, double *x, int32_t *its_out, dou
       pc_apply_vec(c, V[j], zj);
       ++napply;
       system_matvec(c, zj, w);
+      // Several ranks: ||w||^2 - sum h^2 from the single reduction presumes an orthonormal basis; classical
+      // Gram-Schmidt loses orthogonality like (residual reduction)^2 * eps, so the fused norm is used while
+      // the reduction inside the cycle is below 1e4 (norm error < 1e-6 relative) and the explicit norm with
+      // its own all-reduce afterwards.  Decided from the last residual estimate seen: identical on all ranks.
+      const bool pythagoras = c.nranks > 1 && !c.gmres_two_reductions && last_res >= 1e-4 * beta;
       {
         // classical Gram-Schmidt, one reduction
         StageTimer tgs(c, "FENaPack: GMRES orthogonalization");
@@ -259,6 +268,7 @@ static void solve_impl(Ctx &c, const double *b, double *x, int32_t *its_out, dou
       if (near || j + 1 == m || c.timers_on || c.gmres_sync) cycle_over = consume();
     }
     while (!cycle_over && seen < enq) cycle_over = consume();
+    if (cancelled) c.gmres_two_reductions = true;
     // y = H^-1 g (back substitution on the device) ; x += Z y  or  x += M^-1 (V y)
     double *ydev = c.red_out.p;   // reuse the h column slot
     backsolve_kernel<<<1, 32, 0, c.stream>>>(jdone, m, Hd, g, ydev);
@@ -274,7 +284,7 @@ static void solve_impl(Ctx &c, const double *b, double *x, int32_t *its_out, dou
       vec_axpy(c, n, 1.0, c.kr_x.p, x);
     }
     *its_out = its; *rnorm_out = res; *napply_out = napply;
-    if (converged || its >= c.max_it) break;
+    if (converged || (its >= c.max_it && !cancelled)) break;
     // restart: r = b - A x
     system_matvec(c, x, w);
     vec_axpby(c, n, 1.0, b, -1.0, w, w);
@@ -296,16 +306,7 @@ static void solve_impl(Ctx &c, const double *b, double *x, int32_t *its_out, dou
 void solve_fgmres(Ctx &c, const double *b, double *x, int32_t *its_out, double *rnorm_out, int32_t *napply_out) {
   StageTimer t(c, "FENaPack: PCDKSP solve");
   FNP_REQUIRE(c.is_setup, FNP_ERR_STATE, "fnp_solve before fnp_setup");
-  try {
-    solve_impl(c, b, x, its_out, rnorm_out, napply_out);
-  } catch (const Cancellation &) {
-    // the norm from the single reduction lost its digits (w almost in the span of the basis; every
-    // rank sees the same all-reduced numbers and takes the same decision): redo the solve with the
-    // explicit norm and its second all-reduce, and keep that setting for this context
-    FNP_CUDA(cudaStreamSynchronize(c.stream));
-    c.gmres_two_reductions = true;
-    solve_impl(c, b, x, its_out, rnorm_out, napply_out);
-  }
+  solve_impl(c, b, x, its_out, rnorm_out, napply_out);
 }
 
 }  // namespace fnp

@@ -299,7 +299,7 @@ class PCDKrylovSolver(object):
     """Counterpart of the reference's ``dolfin.PETScKrylovSolver`` subclass
     (field_split.py:153-187)."""
 
-    def __init__(self, comm=None, device=0):
+    def __init__(self, comm=None, device=None):
         self._ksp = PCDKSP(comm=comm, device=device)
         self.parameters = {"relative_tolerance": 1e-6, "absolute_tolerance": 1e-50, "maximum_iterations": 10000,
                            "error_on_nonconvergence": True}

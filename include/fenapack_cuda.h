@@ -217,6 +217,11 @@ int fnp_get_residual_history(fnp_context *ctx, double *out, int32_t capacity);
  * coarsens the scalar operator S only; the AMG introspection below then returns the
  * levels of S.  Option fnp_kronecker 0 (before fnp_set_pattern) disables the detection. */
 int fnp_operator_block_size(fnp_context *ctx, int which, int32_t *bs);
+/* The derived PCDR operator Rp = Bt^T diag(Mu)^-1 Bt as the library assembled it (PCDInterface.
+ * _build_approx_Ap, field_split_backend.py:142-166): this rank's rows, GLOBAL column ids.  Sizes from
+ * fnp_rp_info.  Lets a checker build its own hierarchy from bit-identical values on several ranks. */
+int fnp_rp_info(fnp_context *ctx, int64_t *nrows_local, int64_t *nnz);
+int fnp_rp_get(fnp_context *ctx, int32_t *rowptr, int32_t *colidx_global, double *values);
 int fnp_amg_num_levels(fnp_context *ctx, int which, int32_t *levels);
 int fnp_amg_level_info(fnp_context *ctx, int which, int level, int kind, int64_t *nrows,
                        int64_t *ncols, int64_t *nnz, double *rho);

@@ -79,6 +79,7 @@ def device_run(comm, rank, world, variant):
     asm = fp.PCDAssembler(pm.a, pm.L, [], pm.a_pc, ap=pm.ap, kp=pm.kp, mp=pm.mp, bcs_pcd=pm.bc_pcd, function_space=pm.W)
     linear_solver = fp.PCDKrylovSolver(comm=comm)
     linear_solver.parameters["relative_tolerance"] = 1e-8
+    linear_solver.parameters["maximum_iterations"] = 600          # a stagnating solve fails fast instead of spinning
     linear_solver.set_from_options()
     solver = fp.PCDNewtonSolver(linear_solver)
     solver.parameters["relative_tolerance"] = 1e-6
@@ -112,6 +113,9 @@ def device_run(comm, rank, world, variant):
 
 
 def main():
+    import faulthandler
+    # a hang (a collective one rank never reaches) reports where it is stuck and ends the run
+    faulthandler.dump_traceback_later(int(os.environ.get("FNP_TEST_HANG_S", "240")), exit=True)
     host_only = "--host-only" in sys.argv
     variant = next((a for a in sys.argv[1:] if a.startswith("BRM")), "BRM1")
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])

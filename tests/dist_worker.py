@@ -99,8 +99,18 @@ def parity_check(rank, world, local, variant="BRM1", extra_options=None, p2p=Non
         v = rng.standard_normal(prob.n_p)
         out["rp_spmv_relerr"] = relerr(ctx.spmv(capi.MAT_RP, v[p0:p1], p1 - p0), (Rp @ v)[p0:p1])
         assert out["rp_spmv_relerr"] <= 1e-12, ("Rp", out["rp_spmv_relerr"])
-        Hr = oamg.build_hierarchy(Rp, blocks=pb, replicate_size=repl)
+        # the hierarchy of Rp from the values the library assembled (the cross-rank sum rounds differently from
+        # the serial product, and aggregation decisions on a structured mesh are ties): gather its rows
+        import scipy.sparse as sp
+        parts = [None] * world
+        dist.all_gather_object(parts, ctx.rp_local_rows(prob.n_p))
+        Rp_lib = sp.vstack(parts).tocsr()
+        Rp_lib.sort_indices()
+        assert abs(Rp_lib - Rp).max() <= 1e-12 * abs(Rp).max()
+        Hr = oamg.build_hierarchy(Rp_lib, blocks=pb, replicate_size=repl)
         pc = pa.PCDPreconditioner(prob, "iterative", amg_u=Hu, amg_p=Hp, pcdr=True, amg_r=Hr)
+        out["rp_solve_relerr"] = relerr(ctx.rp_solve(v[p0:p1]), pc.solve_Rp(v)[p0:p1])
+        assert out["rp_solve_relerr"] <= 1e-9, ("rp_solve", out["rp_solve_relerr"])
     else:
         pc = pa.PCDPreconditioner(prob, "iterative", amg_u=Hu, amg_p=Hp)
     b = rng.standard_normal(prob.n_p)
@@ -160,6 +170,9 @@ def parity_check(rank, world, local, variant="BRM1", extra_options=None, p2p=Non
 
 
 def main():
+    import faulthandler
+    # a hang (a collective one rank never reaches) reports where it is stuck and ends the run
+    faulthandler.dump_traceback_later(int(os.environ.get("FNP_TEST_HANG_S", "240")), exit=True)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
