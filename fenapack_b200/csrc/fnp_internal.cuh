@@ -473,8 +473,8 @@ struct Ctx {
   int64_t halo_split_rows = 50000;   // operators with at least this many rows are split into interior / boundary rows
                                      // (interior rows overlap the exchange); smaller ones wait in one kernel
   bool split_rows(int64_t nrows) const { return overlap || (p2p && nrows >= halo_split_rows); }
-  int p2p = 1;                  // 2: as 1, and the pack + remote-store kernel of a split operator runs on a forked stream
-                                // beside the interior rows;
+  int p2p = 2;                  // 2 (default): as 1, and the pack + remote-store kernel of a split operator runs on a forked
+                                // stream beside the interior rows (53 M dofs on 8 GPUs: 48.1 ms against 56.1 ms with NCCL);
                                 // 1: peer-memory halo exchange (cudaIpc stores + flags, wait fused into the consumer
                                 // kernel, device-resident sequence numbers); 0: NCCL send/recv
   DevBuf<int> p2p_err;          // set by a timed-out flag wait
