@@ -485,12 +485,14 @@ def b200_arm(args):
             roof["share_of_step"] = e["ms"] / tot
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     roof["traffic"] = None
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:
+        # DRAM bytes per launch of this kernel from the ncu --set full capture at the same size (one rank)
         try:
             tj = json.load(open(tpath))
-            roof["traffic"] = tj.get("spmv_A00_dram_bytes_per_launch", {}).get(str(prob.ndofs_global)) \
-                if isinstance(tj.get("spmv_A00_dram_bytes_per_launch"), dict) else None
+            roof["traffic"] = tj.get("spmv_A00_dram_bytes_per_launch", {}).get(str(prob.ndofs_global))
             roof["traffic_source"] = tj.get("source")
+            roof["traffic_note"] = "captured on the store-epilogue launch (no extra epilogue vectors: 12 B per stored entry + row " \
+                                   "pointers + x + y); bytes_per_launch is the mean over the five launch kinds of an iteration"
         except Exception:
             pass
     result["roofline"] = roof

@@ -754,7 +754,13 @@ static void spmv_launch_bs(Ctx &c, const DevCsr &A, const double *x, const Epi &
 
 template <class Epi>
 static void spmv_launch(Ctx &c, const DevCsr &A, const double *x, const Epi &epi) {
-  if (A.nrows == 0) return;
+  if (A.nrows == 0) {
+    // a rank without rows of this operator still owns entries of x that its neighbours need: the
+    // exchange is collective (found with a partition that gave one rank no pressure dofs at all --
+    // its neighbour waited forever for the velocity ghosts of the divergence block)
+    if (A.halo) halo_exchange(c, *A.halo, x, c.stream, c.comm);
+    return;
+  }
   switch (A.bs) {
     case 1: spmv_launch_bs<1, Epi>(c, A, x, epi); break;
     case 2: spmv_launch_bs<2, Epi>(c, A, x, epi); break;
@@ -1004,7 +1010,8 @@ void multi_axpy_norm_ptrs(Ctx &c, int64_t n, const double *const *Vptrs_dev, int
   const int nblk = red_blocks(c, n);
   StageTimer kt(c, "maxpy+norm", 2, 8.0 * n * (nvec + 2));
   c.red_partial.ensure((size_t)nblk);
-  maxpy_norm_kernel<<<nblk, RED_THREADS, nvec * sizeof(double), c.stream>>>(n, Vptrs_dev, nvec, h_dev, w, c.red_partial.p);
+  // + 16 bytes: the compiler pairs the coefficient loads (16-byte shared loads) and may touch one double past the last
+  maxpy_norm_kernel<<<nblk, RED_THREADS, (nvec + 2) * sizeof(double), c.stream>>>(n, Vptrs_dev, nvec, h_dev, w, c.red_partial.p);
   FNP_LAUNCH_CHECK(c);
   reduce_partials_kernel<<<1, 128, 0, c.stream>>>(c.red_partial.p, nblk, nrm2_dev);
   FNP_LAUNCH_CHECK(c);
@@ -1025,7 +1032,7 @@ maxpy_kernel(int64_t n, const double *const *__restrict__ Z, int nvec, const dou
 
 void multi_axpy_ptrs(Ctx &c, int64_t n, const double *const *Zptrs_dev, int nvec, const double *y_dev, double *x) {
   if (nvec <= 0 || n <= 0) return;
-  maxpy_kernel<<<red_blocks(c, n), RED_THREADS, nvec * sizeof(double), c.stream>>>(n, Zptrs_dev, nvec, y_dev, x);
+  maxpy_kernel<<<red_blocks(c, n), RED_THREADS, (nvec + 2) * sizeof(double), c.stream>>>(n, Zptrs_dev, nvec, y_dev, x);
   FNP_LAUNCH_CHECK(c);
 }
 
