@@ -295,6 +295,64 @@ class PCDKSP(object):
         return self._ctx
 
 
+class PCDKSPPython(object):
+    """``KSPPYTHON`` context around ``PCDKSP``: the entry point for a PETSc driver that OWNS its KSP
+    -- a SNES (defcon's ``SNUFLSolver``, reference demo/defcon/navier-stokes.py:252-280, which in the
+    reference replaces ``solver.snes.ksp`` by a ``PCDKSP``) or a TS.  With petsc4py::
+
+        ksp = snes.ksp
+        ksp.setType(PETSc.KSP.Type.PYTHON)
+        ksp.setPythonContext(PCDKSPPython(pcd_assembler))      # or -ksp_python_type with set_assembler()
+
+    PETSc then calls ``create / setFromOptions / setUp / solve`` (petsc4py's python-KSP protocol); the
+    operators are the ones the driver keeps re-assembling in place, so every ``setUp`` after a Jacobian
+    update triggers the value refresh, exactly as ``PCDNewtonSolver`` does through ``PCDKrylovSolver``."""
+
+    def __init__(self, pcd_assembler=None, pcd_pc_class=None, device=None, ksp_factory=None):
+        self._assembler, self._pc_class, self._device = pcd_assembler, pcd_pc_class, device
+        self._factory = ksp_factory or PCDKSP
+        self._inner = None
+
+    def set_assembler(self, pcd_assembler, pcd_pc_class=None):
+        self._assembler, self._pc_class = pcd_assembler, pcd_pc_class
+
+    def inner(self):
+        return self._inner
+
+    # -- python-KSP protocol (called by PETSc) -----------------------------------
+    def create(self, ksp):
+        self._inner = self._factory(comm=getattr(ksp, "comm", None), device=self._device)
+
+    def setFromOptions(self, ksp):
+        if self._inner._ctx is None:                       # the prefix is frozen by init_pcd
+            self._inner.setOptionsPrefix(ksp.getOptionsPrefix() or "")
+        self._inner.setFromOptions()
+
+    def setUp(self, ksp):
+        A, P = ksp.getOperators()
+        self._inner.setOperators(A, P)
+        if self._inner._ctx is None:
+            if self._assembler is None:
+                raise RuntimeError("PCDKSPPython: no PCDAssembler given (constructor argument or set_assembler)")
+            self._inner.init_pcd(self._assembler, self._pc_class)
+
+    def solve(self, ksp, b, x):
+        try:
+            rtol, atol, _, max_it = ksp.getTolerances()
+            self._inner.setTolerances(rtol=rtol, atol=atol, max_it=max_it)
+        except AttributeError:
+            pass
+        its = self._inner.solve(b, x)
+        for name, val in (("setIterationNumber", its), ("setResidualNorm", self._inner.getResidualNorm()),
+                          ("setConvergedReason", self._inner.getConvergedReason())):
+            if hasattr(ksp, name):
+                getattr(ksp, name)(val)
+
+    def view(self, ksp, viewer=None):
+        print("PCDKSPPython: PCD-preconditioned (F)GMRES on the device, %d iterations in the last solve"
+              % (self._inner.getIterationNumber() if self._inner is not None else 0))
+
+
 class PCDKrylovSolver(object):
     """Counterpart of the reference's ``dolfin.PETScKrylovSolver`` subclass
     (field_split.py:153-187)."""

@@ -402,3 +402,91 @@ def test_krylov_operator_is_the_users_A_not_P():
     ksp.setTolerances(rtol=1e-30, atol=1e-6 * np.linalg.norm(b.array))
     ksp.solve(b, x)
     assert ksp.getConvergedReason() == 3
+
+
+def test_ksp_python_context_protocol():
+    """PCDKSPPython (the KSPPYTHON context for a SNES that owns its KSP, reference
+    demo/defcon/navier-stokes.py:252-280): PETSc's call sequence create -> setFromOptions -> setUp -> solve,
+    repeated setUp/solve after every Jacobian update.  Wiring only (a recording stand-in for PCDKSP): the
+    prefix is taken before init_pcd and left alone afterwards, init_pcd happens exactly once, operators are
+    re-set at every setUp, tolerances / iteration count / reason travel between the two objects."""
+    from fenapack_b200.field_split import PCDKSPPython
+    calls = []
+
+    class FakeInner:
+        def __init__(self, comm=None, device=None):
+            self._ctx = None
+            calls.append(("new", comm, device))
+
+        def setOptionsPrefix(self, p):
+            calls.append(("prefix", p))
+
+        def setFromOptions(self):
+            calls.append(("fromoptions",))
+
+        def setOperators(self, A, P):
+            calls.append(("operators", A, P))
+
+        def init_pcd(self, asm, cls):
+            self._ctx = object()
+            calls.append(("init_pcd", asm, cls))
+
+        def setTolerances(self, rtol=None, atol=None, max_it=None):
+            calls.append(("tol", rtol, atol, max_it))
+
+        def solve(self, b, x):
+            calls.append(("solve", b, x))
+            return 7
+
+        def getResidualNorm(self):
+            return 1e-9
+
+        def getConvergedReason(self):
+            return 2
+
+        def getIterationNumber(self):
+            return 7
+
+    class FakeKSP:
+        comm = "COMM"
+
+        def __init__(self):
+            self.its = self.reason = self.rnorm = None
+
+        def getOptionsPrefix(self):
+            return "ns_"
+
+        def getOperators(self):
+            return ("A", "P")
+
+        def getTolerances(self):
+            return (1e-7, 1e-50, 1e5, 300)
+
+        def setIterationNumber(self, n):
+            self.its = n
+
+        def setConvergedReason(self, r):
+            self.reason = r
+
+        def setResidualNorm(self, r):
+            self.rnorm = r
+
+    ksp = FakeKSP()
+    ctx = PCDKSPPython("ASM", pcd_pc_class="CLS", device=3, ksp_factory=FakeInner)
+    ctx.create(ksp)
+    ctx.setFromOptions(ksp)
+    ctx.setUp(ksp)
+    ctx.solve(ksp, "b", "x")
+    ctx.setFromOptions(ksp)            # SNES calls it again: the prefix must not be touched after init_pcd
+    ctx.setUp(ksp)                     # after a Jacobian update
+    ctx.solve(ksp, "b2", "x2")
+    kinds = [c[0] for c in calls]
+    assert calls[0] == ("new", "COMM", 3)
+    assert kinds.count("init_pcd") == 1 and kinds.count("prefix") == 1 and kinds.count("operators") == 2
+    assert calls[kinds.index("prefix")] == ("prefix", "ns_") and kinds.index("prefix") < kinds.index("init_pcd")
+    assert ("tol", 1e-7, 1e-50, 300) in calls and ("init_pcd", "ASM", "CLS") in calls
+    assert (ksp.its, ksp.reason, ksp.rnorm) == (7, 2, 1e-9)
+    with pytest.raises(RuntimeError):
+        c2 = PCDKSPPython(ksp_factory=FakeInner)
+        c2.create(ksp)
+        c2.setUp(ksp)
