@@ -62,3 +62,26 @@ def test_row_partition_is_a_row_slice():
         assert stacked.nnz == full.scipy(name).nnz
     assert np.allclose(np.concatenate([p.b_u for p in parts]), full.b_u, atol=1e-14)
     assert np.allclose(np.concatenate([p.b_p for p in parts]), full.b_p, atol=1e-14)
+
+
+def test_slab_wise_generation_equals_one_shot():
+    """bench_inputs.generate builds a rank's rows in z-slabs (bounds the generator's device memory at
+    128^3) and chains them: same patterns, values equal to rounding (the summation order of duplicate
+    contributions follows the chunking), same right-hand sides and PCD Dirichlet set -- also for the
+    scalar operator S00 handed to the oracle's hierarchy set-up, with A00 = S00 (x) I_3."""
+    import scipy.sparse as sp
+    for world in (1, 2):
+        for r in range(world):
+            a = bi.OseenBoxProblem(6, 6, 6, rank=r, nranks=world)
+            b = bi.generate(6, 6, 6, rank=r, nranks=world, cells_per_slab=70)
+            assert type(b).__name__ == "MergedProblem"
+            assert (a.u_begin, a.n_u, a.p_begin, a.n_p) == (b.u_begin, b.n_u, b.p_begin, b.n_p)
+            for name in bi.MergedProblem.OPS:
+                x, y = getattr(a, name), getattr(b, name)
+                assert x[0].dtype == y[0].dtype and np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]), name
+                assert np.allclose(x[2], y[2], rtol=0, atol=1e-14 * np.abs(x[2]).max()), name
+            assert np.array_equal(a.bc_idx, b.bc_idx) and np.allclose(a.b_u, b.b_u, atol=1e-15) and np.allclose(a.b_p, b.b_p, atol=1e-15)
+    full = bi.generate(6, 6, 6, cells_per_slab=70)
+    S, A = full.scipy("S00"), full.scipy("A00")
+    d = abs(sp.kron(S, sp.identity(3), format="csr") - A)
+    assert (d.max() if d.nnz else 0.0) == 0.0
