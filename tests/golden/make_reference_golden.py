@@ -12,7 +12,8 @@ The matrices come from oracle/fem.py (the reference assembles them with DOLFIN),
 mixed space with the DOLFIN-like interleaved numbering of oracle.problems.interleaved_index_sets.
 
 Output: tests/golden/ref_pcd_apply.npz -- x, the reference's y per class, the Rp matrix the
-reference builds, and the BC index list its SubfieldBC mapping produces.  tests/test_reference_golden.py
+reference builds, and the BC index list its SubfieldBC mapping produces; ref_pcd_apply_more.npz -- the
+same for PCDPC_BRM1/2 on BFS level 3 and on a 3D channel (6 x 2 x 3 bricks).  tests/test_reference_golden.py
 checks the oracle against these (CPU) and the CUDA library against them (GPU).  Needs /root/reference:
     python tests/golden/make_reference_golden.py
 """
@@ -146,6 +147,29 @@ def run_assembler(cls, n, forms, bcs, bcs_pcd, x_newton):
     return out
 
 
+def more_problems(variant):
+    """Inputs of the second fixture file: a second BFS size and a 3D problem (row lengths 15 on the
+    pressure space instead of 7, Chebyshev bounds of 3D P1 tetrahedra)."""
+    p0, _ = problems.backward_facing_step(3, nu=NU, variant=variant)
+    x = pa.direct_solver(p0.system_matrix())(p0.rhs())
+    bfs3 = problems.backward_facing_step(3, nu=NU, variant=variant, wind=x[:p0.n_u].reshape(-1, 2))
+    ch3d = problems.channel(6, 2, 3, nu=NU, variant=variant)
+    return {"bfs3": bfs3, "channel3d": ch3d}
+
+
+def more_cases(pcmod, fsb):
+    out = {}
+    rng = np.random.default_rng(11)
+    for cls_name, variant in (("PCDPC_BRM1", "BRM1"), ("PCDPC_BRM2", "BRM2")):
+        for case, (prob, space) in more_problems(variant).items():
+            x = rng.standard_normal(prob.n_p)
+            y, extra = reference_apply(pcmod, fsb, cls_name, prob, space, 0.0, x, deep=True)
+            out[f"{case}_{cls_name}_x"], out[f"{case}_{cls_name}_y"] = x, y
+            out[f"{case}_{cls_name}_bc_idx"] = extra["bc_idx"]
+            print(case, cls_name, "n_p", prob.n_p, "|y|", np.linalg.norm(y))
+    return out
+
+
 def main():
     asm_mod = rs.load_reference_assembling()
     ref = run_assembler(asm_mod.PCDAssembler, *assembler_inputs())
@@ -166,6 +190,7 @@ def main():
             out[f"{cls_name}_{k}"] = v
         print(cls_name, "n_p", prob.n_p, "|y|", np.linalg.norm(y_shallow), "refresh assembles", list(extra["refresh_assembles"]))
     np.savez_compressed(os.path.join(HERE, "ref_pcd_apply.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "ref_pcd_apply_more.npz"), **more_cases(pcmod, fsb))
 
 
 if __name__ == "__main__":
