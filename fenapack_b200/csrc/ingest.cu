@@ -354,7 +354,8 @@ static void launch_values(Ctx &c, DevCsr &A, const int32_t *rowptr_exp, const in
   double *dinv = nullptr;
   if (want_dinv) {
     A.dinv.ensure((size_t)A.nrows * BS);
-    FNP_CUDA(cudaMemsetAsync(A.dinv.p, 0, (size_t)A.nrows * BS * sizeof(double), c.stream));   // rows without a stored diagonal
+    if (A.nrows > 0)      // (a rank may own no row of an operator)
+      FNP_CUDA(cudaMemsetAsync(A.dinv.p, 0, (size_t)A.nrows * BS * sizeof(double), c.stream));   // rows without a stored diagonal
     dinv = A.dinv.p;
   }
   if (A.sell) {
