@@ -127,6 +127,32 @@ def _f64(a):
     return a
 
 
+def merge_mpiaij(diag, offdiag, garray, col_start):
+    """Local rows of a PETSc MPIAIJ matrix from its two sequential blocks, as the library wants them
+    (global column ids, one CSR).  ``diag`` / ``offdiag`` = ``(indptr, indices, data-or-None)`` of the
+    diagonal block (columns local to the owned column range starting at ``col_start``) and of the
+    off-diagonal block (compressed columns, ``garray[j]`` = global id) -- what ``MatMPIAIJGetSeqAIJ``
+    hands out.  Returns ``(indptr, indices, order)``: the merged pattern and the position of every merged
+    entry in ``concatenate([diag.data, offdiag.data])``, so that a value refresh is
+    ``concatenate([a_d, a_o])[order]`` without touching the pattern again (the MAT_REUSE_MATRIX path,
+    field_split_backend.py:331-334)."""
+    ia_d, ja_d = np.asarray(diag[0], dtype=np.int64), np.asarray(diag[1], dtype=np.int64)
+    ia_o, ja_o = np.asarray(offdiag[0], dtype=np.int64), np.asarray(offdiag[1], dtype=np.int64)
+    garray = np.asarray(garray, dtype=np.int64)
+    n = ia_d.size - 1
+    if ia_o.size - 1 != n:
+        raise ValueError("diagonal and off-diagonal blocks must have the same number of rows")
+    rows = np.concatenate([np.repeat(np.arange(n), np.diff(ia_d)), np.repeat(np.arange(n), np.diff(ia_o))])
+    cols = np.concatenate([ja_d + int(col_start), garray[ja_o] if ja_o.size else ja_o])
+    order = np.lexsort((cols, rows))                    # row major, ascending global column
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(indptr, rows + 1, 1)
+    indptr = np.cumsum(indptr)
+    if indptr[-1] >= 2 ** 31:
+        raise ValueError("more than 2^31 local entries")
+    return indptr.astype(np.int32), cols[order].astype(np.int32), order
+
+
 def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _check(load().fnp_nccl_unique_id(buf))
@@ -202,6 +228,21 @@ class Context:
         A = A.tocsr()
         self.set_pattern(which, A.indptr, A.indices)
         self.set_values(which, A.data)
+
+    def set_matrix_mpiaij(self, which, diag, offdiag, garray, col_start):
+        """Upload the local rows of an MPIAIJ matrix given as its diagonal / off-diagonal blocks
+        (``merge_mpiaij``); the entry order is remembered for ``set_values_mpiaij``."""
+        indptr, indices, order = merge_mpiaij(diag, offdiag, garray, col_start)
+        if not hasattr(self, "_mpiaij_order"):
+            self._mpiaij_order = {}
+        self._mpiaij_order[which] = order
+        self.set_pattern(which, indptr, indices)
+        self.set_values_mpiaij(which, diag[2], offdiag[2])
+
+    def set_values_mpiaij(self, which, diag_values, offdiag_values):
+        """Value refresh of an operator uploaded with ``set_matrix_mpiaij`` (same pattern)."""
+        vals = np.concatenate([_f64(diag_values).ravel(), _f64(offdiag_values).ravel()])
+        self.set_values(which, vals[self._mpiaij_order[which]])
 
     def set_bc(self, idx, values):
         idx = np.ascontiguousarray(idx, dtype=np.int32)

@@ -89,3 +89,41 @@ def test_galerkin_plan_cxx_matches_oracle(harness):
     R, r = _args(H.levels[0].P.T)
     bad, c = _args(sp.identity(P.shape[1], format="csr"))
     assert harness.plan_build(C.c_int64(A.shape[0]), C.c_int64(P.shape[1]), *[_ptr(v) for v in a + p + r + c]) == -1
+
+
+def test_mpiaij_block_merge():
+    """capi.merge_mpiaij: the diagonal / off-diagonal SeqAIJ blocks of a PETSc MPIAIJ matrix (local column
+    ids in the diagonal block, compressed columns + garray in the off-diagonal one) merged into the local
+    rows with global, ascending column ids the library ingests; the returned order refreshes values
+    without touching the pattern."""
+    from fenapack_b200 import capi
+    rng = np.random.default_rng(3)
+    n_glob, r0, r1 = 60, 20, 45                     # this rank owns rows / columns [20, 45)
+    A = sp.random(n_glob, n_glob, density=0.15, random_state=4, format="csr")
+    A.data[:] = rng.standard_normal(A.nnz)
+    loc = A[r0:r1, :].tocsr()
+    loc.sort_indices()
+    own = (loc.indices >= r0) & (loc.indices < r1)
+    rows = np.repeat(np.arange(r1 - r0), np.diff(loc.indptr))
+
+    def block(mask, colmap):
+        M = sp.csr_matrix((loc.data[mask], (rows[mask], colmap(loc.indices[mask]))), shape=(r1 - r0, n_glob))
+        M.sort_indices()
+        return M
+    D = block(own, lambda c: c - r0)
+    garray = np.unique(loc.indices[~own])            # PETSc: sorted global ids of the compressed columns
+    O = block(~own, lambda c: np.searchsorted(garray, c))
+    indptr, indices, order = capi.merge_mpiaij((D.indptr, D.indices, D.data), (O.indptr, O.indices, O.data), garray, r0)
+    assert indptr.dtype == np.int32 and indices.dtype == np.int32
+    assert np.array_equal(indptr, loc.indptr) and np.array_equal(indices, loc.indices)
+    assert np.array_equal(np.concatenate([D.data, O.data])[order], loc.data)
+    # value refresh: new numbers on the same blocks
+    loc2 = loc.copy()
+    loc2.data = rng.standard_normal(loc.nnz)
+    D2, O2 = loc2.data[own], loc2.data[~own]         # row-major inside each block == the blocks' CSR order
+    assert np.array_equal(np.concatenate([D2, O2])[order], loc2.data)
+    # an empty off-diagonal block (single rank) and mismatching blocks
+    i2, j2, o2 = capi.merge_mpiaij((D.indptr, D.indices, D.data), (np.zeros(r1 - r0 + 1, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0)), np.zeros(0, dtype=np.int64), r0)
+    assert np.array_equal(i2, D.indptr) and np.array_equal(j2, D.indices + r0)
+    with pytest.raises(ValueError):
+        capi.merge_mpiaij((D.indptr, D.indices, D.data), (O.indptr[:-1], O.indices, O.data), garray, r0)
