@@ -17,7 +17,7 @@ GPUs (rows of all operators partitioned in contiguous z-slabs), as configs[4]
 asks.  `--scaling weak --n1 64` keeps 6.7 M dofs per GPU instead
 (n = round(n1 * N^(1/3))).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--scaling strong|weak] [--n 128] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--scaling strong|weak] [--bricks 128] [--impl reference]
 """
 from __future__ import annotations
 
@@ -83,7 +83,9 @@ def parse_args():
     ap.add_argument("--workload", default="cavity3d", choices=["cavity3d", "channel3d"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the same n^3 system on every N (default); weak: n = round(n1 * N^(1/3))")
-    ap.add_argument("--n", type=int, default=128, help="bricks per side of the whole system (strong scaling)")
+    ap.add_argument("--bricks", "--n", dest="n", type=int, default=128,
+                    help="bricks per side of the whole system (strong scaling); use --bricks under torchrun, whose own "
+                         "parser claims the abbreviation --n")
     ap.add_argument("--n1", type=int, default=64, help="bricks per side on one GPU (weak scaling base)")
     ap.add_argument("--no-refresh", action="store_true", help="skip the value-refresh timing")
     ap.add_argument("--no-dist-parity", action="store_true", help="skip the small oracle-checked problem at N > 1")
